@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Headline benchmark: grid-points/s, forward+backward, Darcy 141^2 Galerkin-transformer (BASELINE C3).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload ("darcy141_galerkin10_sc2d_b8"): FourierTransformer2D with the reference's ex2_darcy
+configuration (config.yml:41-80) at the reference's own profiling protocol
+(examples/ex2_memory_profile.py:58-71): fine grid 141x141, attention on the 43x43 coarse grid,
+d_model 128, 4 heads, 10 Galerkin encoder layers, 2 SpectralConv2d (32 ch, 12 modes), batch 8
+per GPU, fp32, synthetic N(0,1) inputs, loss ((preds-target)^2).mean(), model in training mode
+with the config's dropouts and the reference's always-on attention dropout ('reference' mode).
+A step = one forward + backward over one batch (+ one flat-bucket gradient all-reduce when N>1).
+
+Lines printed (rank 0): one JSON object, see the keys in `main`.
+  value  : device-timed (CUDA events per step, L2 flushed between steps), inputs resident in HBM
+  e2e    : same metric through the public module API with pinned HOST inputs; H2D copies of the
+           step's inputs and the D2H read of the loss are inside the timed region
+  roofline / kernels : per-launch CUDA-event attribution pass run right after the timed region
+  cpu_baseline : the oracle (CPU restatement of the reference) timed on this box's host cores
+--impl reference : the oracle on CPU only, same metric/config (the reference is pure PyTorch and
+  cannot travel to the GPU box; the oracle is pinned to it by tests/golden).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_FINE, N_COARSE, BATCH = 141, 43, 8
+POINTS_PER_SAMPLE = N_FINE * N_FINE
+WORKLOAD = "darcy141_galerkin10_sc2d_b8"
+METRIC = "grid-points/sec fwd+bwd, Darcy 141^2 Galerkin encoder"
+
+
+def c3_config(dropout_free=False):
+    """ex2_darcy section of the reference's config.yml with the BASELINE overrides
+    (10 encoder layers; scaler sizes from get_scaler_sizes(141, 43); ex2_darcy.py:67-82)."""
+    from galerkin_transformer_b200.utils import scaler_sizes
+    down, up = scaler_sizes(N_FINE, N_COARSE)
+    cfg = dict(node_feats=1, pos_dim=2, n_targets=1, n_hidden=128, num_feat_layers=0,
+               num_encoder_layers=10, n_head=4, dim_feedforward=256, feat_extract_type=None,
+               attention_type="galerkin", xavier_init=0.01, diagonal_weight=0.01, symmetric_init=False,
+               layer_norm=False, attn_norm=True, norm_eps=1e-7, batch_norm=False,
+               return_attn_weight=False, return_latent=False, decoder_type="ifft2", spacial_dim=2,
+               spacial_fc=True, upsample_mode="interp", downsample_mode="interp", freq_dim=32,
+               boundary_condition="dirichlet", num_regressor_layers=2, fourier_modes=12,
+               regressor_activation="silu", downscaler_activation="relu", upscaler_activation="silu",
+               last_activation=True, dropout=0.0, downscaler_dropout=0.05, upscaler_dropout=0.0,
+               ffn_dropout=0.05, encoder_dropout=0.05, decoder_dropout=0.0, debug=False,
+               downscaler_size=down, upscaler_size=up)
+    if dropout_free:
+        for k in ("dropout", "downscaler_dropout", "upscaler_dropout", "ffn_dropout", "encoder_dropout",
+                  "decoder_dropout"):
+            cfg[k] = 0.0
+    return cfg
+
+
+def c3_inputs(bsz, device, seed=1127802, pin=False):
+    """node, pos, grid, target as the reference's datasets shape them (ft.py:643-651)."""
+    g = torch.Generator().manual_seed(seed)
+    node = torch.randn(bsz, N_FINE, N_FINE, 1, generator=g)
+    target = torch.randn(bsz, N_FINE, N_FINE, 1, generator=g)
+    gc = torch.linspace(0, 1, N_COARSE)
+    pos = torch.stack(torch.meshgrid(gc, gc, indexing="ij"), -1).reshape(1, -1, 2).repeat(bsz, 1, 1)
+    gf = torch.linspace(0, 1, N_FINE)
+    grid = torch.stack(torch.meshgrid(gf, gf, indexing="ij"), -1)[None].repeat(bsz, 1, 1, 1)
+    out = [node, pos.contiguous(), grid.contiguous(), target]
+    if pin:
+        return [t.pin_memory() for t in out]
+    return [t.to(device) for t in out]
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, bsz):
+    """fwd+bwd of the oracle's FourierTransformer2D restatement on the host cores, faithful
+    attention dropout; returns (grid-points/s, seconds per step, threads)."""
+    from oracle import galerkin_oracle as O
+    import galerkin_transformer_b200 as G
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(1127802)
+    cfg = c3_config()
+    model = G.FourierTransformer2D(**cfg)          # parameter container only (never run on CPU)
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+    node, pos, grid, target = c3_inputs(bsz, "cpu")
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        pred = O.fourier_transformer_2d(sd, cfg, node, pos, grid, attn_dropout=True)
+        loss = ((pred - target) ** 2).mean()
+        grads = torch.autograd.grad(loss, [v for v in sd.values() if v.requires_grad])
+        loss.item()
+        del grads
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return bsz * POINTS_PER_SAMPLE / sec, sec, threads
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out = ""
+        sm, smax, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                 f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(smax) if smax else None,
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"],
+                    bf16_tflops_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+def kernel_table(summary, steps, peaks):
+    """Per kernel family: launches/step, ms/step, achieved GB/s and TFLOP/s on ALGORITHMIC work."""
+    rows = []
+    tf32_peak = peaks["bf16_tflops_sustained"] / 2.0        # dense TF32 = 1/2 dense bf16 on tcgen05
+    ridge = tf32_peak * 1e12 / (peaks["hbm_gbs"] * 1e9)
+    for fam, a in summary.items():
+        ms = a["ms"] / steps
+        if ms <= 0:
+            continue
+        gbs = a["bytes"] / steps / (ms * 1e-3) / 1e9
+        tfs = a["flops"] / steps / (ms * 1e-3) / 1e12
+        ai = a["flops"] / max(a["bytes"], 1.0)
+        bound = "tensor" if ai > ridge else "hbm"
+        frac = tfs / tf32_peak if bound == "tensor" else gbs / peaks["hbm_gbs"]
+        rows.append(dict(kernel=fam, launches_per_step=a["launches"] / steps, ms_per_step=round(ms, 4),
+                         alg_gbs=round(gbs, 1), alg_tflops=round(tfs, 3), bound=bound, frac=round(frac, 4),
+                         ms_per_launch=round(a["ms"] / a["launches"], 5),
+                         alg_bytes_per_launch=a["bytes"] / a["launches"],
+                         alg_flops_per_launch=a["flops"] / a["launches"]))
+    rows.sort(key=lambda r: -r["ms_per_step"])
+    return rows, tf32_peak
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--attn-dropout", default="reference", choices=["reference", "off"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = dict(workload=WORKLOAD, grid="141x141 fine / 43x43 attention", batch_per_gpu=BATCH,
+                  global_batch=BATCH * world, encoder_layers=10, d_model=128, heads=4,
+                  decoder="2x SpectralConv2d(32, modes 12)", parallelism=f"dp{world}",
+                  dropout="config.yml ex2_darcy (ffn/encoder 0.05, downscaler 0.05), attention p=0.5 "
+                          + args.attn_dropout,
+                  l2="256 MiB buffer written between timed steps (L2 flush)")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        bsz = BATCH if args.steps + args.warmup <= 24 else 2
+        val, sec, threads = cpu_reference_run(args.steps, args.warmup, bsz)
+        sample = f"{args.steps} fwd+bwd steps of the C3 model on a batch of {bsz} (CPU oracle, fp32, faithful attention dropout)"
+        print(json.dumps(dict(
+            impl="reference", metric=METRIC, value=val, unit="grid-points/s", n_gpus=args.gpus, steps=args.steps,
+            warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+            dtype="f32", data="synthetic", config=config,
+            cpu_baseline=dict(value=val, unit="grid-points/s", cores=threads, kind="port", sample=sample),
+            e2e=dict(value=val, unit="grid-points/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+        return
+
+    import torch.distributed as dist
+    import galerkin_transformer_b200 as G
+    from galerkin_transformer_b200 import _lib, functional as GF
+    from galerkin_transformer_b200.parallel import FlatGradBucket
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(1127802 + rank)
+    cfg = c3_config()
+    torch.manual_seed(1127802)                      # identical replicas
+    model = G.FourierTransformer2D(**cfg).to(dev)
+    model.train()
+    G.set_attn_dropout(model, args.attn_dropout)
+    torch.manual_seed(1127802 + rank)               # per-rank dropout streams / data
+    bucket = FlatGradBucket(model)
+    node, pos, grid, target = c3_inputs(BATCH, dev, seed=1127802 + rank)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def step(n_, p_, g_, t_):
+        bucket.zero()
+        pred = model(n_, None, p_, g_)["preds"]
+        loss = ((pred - t_) ** 2).mean()
+        loss.backward()
+        bucket.all_reduce()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(node, pos, grid, target)
+    barrier()
+
+    # ---- timed region: K steps, device-timed per step, L2 flushed in between -----------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    launches0 = _lib.launch_count()
+    barrier()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(float(i))
+        starts[i].record()
+        step(node, pos, grid, target)
+        ends[i].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    gpu_launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = t.item()
+    ms_per_step = total_ms / args.steps
+    value = BATCH * world * POINTS_PER_SAMPLE / (ms_per_step * 1e-3)
+
+    # ---- end to end: pinned host inputs -> H2D -> fwd+bwd -> D2H loss, every step ------------
+    host = c3_inputs(BATCH, dev, seed=1127802 + rank, pin=True)
+    h2d = sum(t_.numel() * t_.element_size() for t_ in host)
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    e2e_steps = args.steps
+    for _ in range(2):
+        loss_host.copy_(step(*[h.to(dev, non_blocking=True) for h in host]).detach(), non_blocking=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        loss_host.copy_(step(*[h.to(dev, non_blocking=True) for h in host]).detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()        # the user reads the loss every step (utils_ft.py:687)
+        float(loss_host)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = BATCH * world * POINTS_PER_SAMPLE / (t.item() / e2e_steps * 1e-3)
+
+    # ---- attribution pass: per-launch CUDA events on the launching stream --------------------
+    kernels, roofline = [], None
+    if rank == 0:
+        peaks = measured_peaks()
+        prof_steps = min(args.steps, 5)
+        GF.Profiler.reset()
+        GF.Profiler.enabled = True
+        tot0, tot1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tot0.record()
+        for _ in range(prof_steps):
+            step(node, pos, grid, target)
+        tot1.record()
+        torch.cuda.synchronize()
+        GF.Profiler.enabled = False
+        kernels, tf32_peak = kernel_table(GF.Profiler.summary(), prof_steps, peaks)
+        native_ms = sum(k["ms_per_step"] for k in kernels)
+        step_ms_prof = tot0.elapsed_time(tot1) / prof_steps
+        top = kernels[0]
+        roofline = dict(kernel=top["kernel"], bound=top["bound"],
+                        achieved=top["alg_tflops"] if top["bound"] == "tensor" else top["alg_gbs"],
+                        peak=tf32_peak if top["bound"] == "tensor" else peaks["hbm_gbs"],
+                        unit="TFLOP/s" if top["bound"] == "tensor" else "GB/s", frac=top["frac"],
+                        traffic=None, share_of_step=round(top["ms_per_step"] / step_ms_prof, 4),
+                        peak_source=f"MEASURED_PEAKS.json ({peaks['source']}); tensor peak = sustained bf16 / 2 "
+                                    "(dense TF32)",
+                        timing=f"CUDA events around every launch, {prof_steps}-step attribution pass after the "
+                               "timed region",
+                        native_ms_per_step=round(native_ms, 3), step_ms_in_pass=round(step_ms_prof, 3))
+    if world > 1:
+        dist.barrier()
+
+    if rank == 0:
+        out = dict(metric=METRIC, value=value, unit="grid-points/s", n_gpus=world, steps=args.steps,
+                   warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True, scaling="weak",
+                   vs_baseline=None, dtype="f32", data="synthetic", config=config, clocks=clocks,
+                   e2e=dict(value=e2e_value, unit="grid-points/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4),
+                   gpu_launches=int(gpu_launches), wall_s_timed_region=round(wall, 3),
+                   grad_bucket_bytes=bucket.nbytes, roofline=roofline, kernels=kernels[:12])
+        if world == 1 and not args.no_cpu_baseline:
+            cval, csec, threads = cpu_reference_run(3, 1, BATCH)
+            out["cpu_baseline"] = dict(value=cval, unit="grid-points/s", cores=threads, kind="port",
+                                       sample="3 fwd+bwd steps (after 1 warm-up) of the same C3 batch-8 workload, "
+                                              "CPU oracle, fp32, faithful attention dropout",
+                                       ms_per_step=csec * 1e3)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

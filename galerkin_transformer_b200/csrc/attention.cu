@@ -1,0 +1,406 @@
+// Softmax-free attention core (Galerkin Q(K^T V)/n and linear-form Fourier (Q K^T) V/(sqrt(d) n)).
+//
+// Layout: tokens stay token-major.  The projection GEMM writes one (T, 3*d_model) buffer
+// [Q | K | V]; head h of each operand is the d_k-wide column slice h*d_k.. of its block.  No
+// head-major transposes, no torch.cat of the position columns, no torch.stack of per-head
+// LayerNorm outputs ever exist in HBM: the kernels read an "augmented head operand"
+//       X~[t, h, :] = [ pos[t, 0..p) , gamma[h] * xhat[t, h, :] + beta[h] ]          (d = p + d_k)
+// straight from the token-major buffers (xhat = the per-head normalised rows written in
+// place by headnorm_fwd, or the raw rows when the operand has no norm).
+//
+// Reference semantics replaced here (scaomath/galerkin-transformer):
+//   libs/layers.py:846-851, 859-864   per-head LayerNorm loop + torch.stack
+//   libs/layers.py:869-874            pos.repeat + torch.cat([pos, x]) for q, k, v
+//   libs/layers.py:723, 728, 733      K^T V, /n, Q.(.)           (linear_attention)
+//   libs/layers.py:730-731            F.dropout(p_attn), p=0.5, always on (mask input)
+//   libs/layers.py:892-894            transpose(1,2).contiguous().view  (head merge)
+#include "common.cuh"
+
+namespace gb200 {
+
+struct HeadOperand {
+    const float* ptr;    // token-major rows
+    int ld;              // row stride (floats)
+    int col0;            // first column of head 0
+    int augmented;       // 1: rows already hold [pos | x] per head (stride d per head)
+    const float* gamma;  // (H, d_k) or null
+    const float* beta;   // (H, d_k) or null
+};
+
+__device__ __forceinline__ float load_aug(const HeadOperand& op, const float* __restrict__ pos, int p,
+                                          int dk, int h, long long t, int i) {
+    if (op.augmented) return op.ptr[t * op.ld + op.col0 + h * (p + dk) + i];
+    if (i < p) return pos[t * p + i];
+    const int c = i - p;
+    float v = op.ptr[t * op.ld + op.col0 + h * dk + c];
+    if (op.gamma) v = v * op.gamma[h * dk + c] + op.beta[h * dk + c];
+    return v;
+}
+
+// -------------------------------------------------------------------------------------------
+// per-head LayerNorm, forward: x -> xhat (in place), rstd (T, H) saved for backward.
+// One CTA stages ROWS token rows (all heads) through shared memory with coalesced loads,
+// then one thread normalises one (token, head) group (biased variance, two-pass).
+// -------------------------------------------------------------------------------------------
+constexpr int HN_ROWS = 32;
+
+__global__ void headnorm_fwd_kernel(float* __restrict__ x, int ld, int col0, long long T, int H, int dk,
+                                    float eps, float* __restrict__ rstd_out) {
+    extern __shared__ float sm[];
+    const int W = H * dk, WS = W + 1;
+    const long long t0 = (long long)blockIdx.x * HN_ROWS;
+    const int nrows = (int)min((long long)HN_ROWS, T - t0);
+    for (int e = threadIdx.x; e < nrows * W; e += blockDim.x) {
+        int r = e / W, c = e % W;
+        sm[r * WS + c] = x[(t0 + r) * ld + col0 + c];
+    }
+    __syncthreads();
+    for (int gidx = threadIdx.x; gidx < nrows * H; gidx += blockDim.x) {
+        int r = gidx / H, h = gidx % H;
+        float* row = sm + r * WS + h * dk;
+        float mean = 0.f;
+        for (int c = 0; c < dk; ++c) mean += row[c];
+        mean /= dk;
+        float var = 0.f;
+        for (int c = 0; c < dk; ++c) { float d = row[c] - mean; var += d * d; }
+        var /= dk;
+        float rs = rsqrtf(var + eps);
+        for (int c = 0; c < dk; ++c) row[c] = (row[c] - mean) * rs;
+        rstd_out[(t0 + r) * H + h] = rs;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nrows * W; e += blockDim.x) {
+        int r = e / W, c = e % W;
+        x[(t0 + r) * ld + col0 + c] = sm[r * WS + c];
+    }
+}
+
+// per-head LayerNorm, backward.  dy (grad w.r.t. gamma*xhat+beta) is overwritten by the grad
+// w.r.t. the raw projection output; per-CTA partial sums of dgamma/dbeta go to `part`.
+__global__ void headnorm_bwd_kernel(float* __restrict__ dy, int lddy, int dcol0,
+                                    const float* __restrict__ xhat, int ldx, int xcol0,
+                                    const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                    long long T, int H, int dk, float* __restrict__ part) {
+    extern __shared__ float sm[];
+    const int W = H * dk, WS = W + 1;
+    float* sdy = sm;
+    float* sxh = sm + HN_ROWS * WS;
+    const long long t0 = (long long)blockIdx.x * HN_ROWS;
+    const int nrows = (int)min((long long)HN_ROWS, T - t0);
+    for (int e = threadIdx.x; e < nrows * W; e += blockDim.x) {
+        int r = e / W, c = e % W;
+        sdy[r * WS + c] = dy[(t0 + r) * lddy + dcol0 + c];
+        sxh[r * WS + c] = xhat[(t0 + r) * ldx + xcol0 + c];
+    }
+    __syncthreads();
+    // dgamma / dbeta partials: one thread per column, fixed row order
+    for (int c = threadIdx.x; c < W; c += blockDim.x) {
+        float sg = 0.f, sb = 0.f;
+        for (int r = 0; r < nrows; ++r) {
+            float d = sdy[r * WS + c];
+            sg += d * sxh[r * WS + c];
+            sb += d;
+        }
+        part[((long long)blockIdx.x * 2 + 0) * W + c] = sg;
+        part[((long long)blockIdx.x * 2 + 1) * W + c] = sb;
+    }
+    __syncthreads();
+    for (int gidx = threadIdx.x; gidx < nrows * H; gidx += blockDim.x) {
+        int r = gidx / H, h = gidx % H;
+        float* d = sdy + r * WS + h * dk;
+        const float* xh = sxh + r * WS + h * dk;
+        const float* gm = gamma + h * dk;
+        float c1 = 0.f, c2 = 0.f;
+        for (int c = 0; c < dk; ++c) {
+            float gd = gm[c] * d[c];
+            c1 += gd;
+            c2 += gd * xh[c];
+        }
+        c1 /= dk; c2 /= dk;
+        float rs = rstd[(t0 + r) * H + h];
+        for (int c = 0; c < dk; ++c) d[c] = rs * (gm[c] * d[c] - c1 - xh[c] * c2);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nrows * W; e += blockDim.x) {
+        int r = e / W, c = e % W;
+        dy[(t0 + r) * lddy + dcol0 + c] = sdy[r * WS + c];
+    }
+}
+
+// out[j][c] (+)= sum_blocks part[blk][j][c]   (j = 0: dgamma, 1: dbeta), fixed order
+__global__ void headnorm_bwd_reduce_kernel(const float* __restrict__ part, int nblocks, int W,
+                                           float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                           int accumulate) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= W) return;
+    float sg = 0.f, sb = 0.f;
+    for (int b = 0; b < nblocks; ++b) {
+        sg += part[((long long)b * 2 + 0) * W + c];
+        sb += part[((long long)b * 2 + 1) * W + c];
+    }
+    dgamma[c] = accumulate ? dgamma[c] + sg : sg;
+    dbeta[c] = accumulate ? dbeta[c] + sb : sb;
+}
+
+// -------------------------------------------------------------------------------------------
+// xty:  P[b,h,s][i][j] = sum_{t in split s} L~[b,t,h,i] * R~[b,t,h,j]          (d x d per head)
+// CTA = one (b,h) x one token split; TC tokens staged per step; 16x16 threads, (DP/16)^2
+// accumulators each.  Partials are summed in fixed order by xty_reduce (deterministic).
+// -------------------------------------------------------------------------------------------
+template <int DP>
+__global__ void __launch_bounds__(256) xty_kernel(HeadOperand L, HeadOperand R, const float* __restrict__ pos,
+                                                  int p, int dk, int H, int n, int nsplit, int chunk,
+                                                  float* __restrict__ part) {
+    constexpr int TC = 32, MT = DP / 16;
+    __shared__ float Ls[TC][DP + 1];
+    __shared__ float Rs[TC][DP + 1];
+    const int d = p + dk;
+    const int bh = blockIdx.y, b = bh / H, h = bh % H, split = blockIdx.x;
+    const int tbeg = split * chunk, tend = min(n, tbeg + chunk);
+    const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
+    float acc[MT][MT];
+#pragma unroll
+    for (int a = 0; a < MT; ++a)
+#pragma unroll
+        for (int c = 0; c < MT; ++c) acc[a][c] = 0.f;
+
+    for (int t0 = tbeg; t0 < tend; t0 += TC) {
+        const int nt = min(TC, tend - t0);
+        for (int e = threadIdx.x; e < TC * DP; e += 256) {
+            int r = e / DP, i = e % DP;
+            float lv = 0.f, rv = 0.f;
+            if (r < nt && i < d) {
+                long long t = (long long)b * n + t0 + r;
+                lv = load_aug(L, pos, p, dk, h, t, i);
+                rv = load_aug(R, pos, p, dk, h, t, i);
+            }
+            Ls[r][i] = lv;
+            Rs[r][i] = rv;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int r = 0; r < TC; ++r) {
+            float lv[MT], rv[MT];
+#pragma unroll
+            for (int a = 0; a < MT; ++a) lv[a] = Ls[r][ty + 16 * a];
+#pragma unroll
+            for (int c = 0; c < MT; ++c) rv[c] = Rs[r][tx + 16 * c];
+#pragma unroll
+            for (int a = 0; a < MT; ++a)
+#pragma unroll
+                for (int c = 0; c < MT; ++c) acc[a][c] = fmaf(lv[a], rv[c], acc[a][c]);
+        }
+        __syncthreads();
+    }
+    float* out = part + ((long long)bh * nsplit + split) * d * d;
+#pragma unroll
+    for (int a = 0; a < MT; ++a)
+#pragma unroll
+        for (int c = 0; c < MT; ++c) {
+            int i = ty + 16 * a, j = tx + 16 * c;
+            if (i < d && j < d) out[i * d + j] = acc[a][c];
+        }
+}
+
+// A[bh][i][j] = scale * sum_s P[bh][s][i][j] * (mask ? 2*mask : 1); optionally also the
+// un-masked value (needed by nothing downstream; kept null) -- fixed summation order.
+__global__ void xty_reduce_kernel(const float* __restrict__ part, int nsplit, int dd, long long total,
+                                  float scale, const unsigned char* __restrict__ mask,
+                                  float* __restrict__ out) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        long long bh = e / dd;
+        int ij = (int)(e % dd);
+        const float* p = part + bh * nsplit * dd + ij;
+        float s = 0.f;
+        for (int k = 0; k < nsplit; ++k) s += p[(long long)k * dd];
+        s *= scale;
+        if (mask) s *= 2.f * (float)mask[e];
+        out[e] = s;
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// xm:  O[b,t,h,j] = sum_i L~[b,t,h,i] * M[b,h][i][j]      (or M^T), token tile x d x d.
+// Output either in augmented layout (T, H*d) -- the head-merged tensor the fc Linear reads --
+// or scattered into a token-major (T, ld) buffer dropping the p position columns (gradients
+// w.r.t. q, k, v: position coordinates carry no gradient).
+// -------------------------------------------------------------------------------------------
+template <int DP>
+__global__ void __launch_bounds__(256) xm_kernel(HeadOperand L, const float* __restrict__ pos,
+                                                 const float* __restrict__ Mat, int transM, int p, int dk,
+                                                 int H, int n, float* __restrict__ out, int ldo, int ocol0,
+                                                 int out_augmented, float oscale) {
+    constexpr int TT = 64, MT = DP / 16;
+    extern __shared__ float sm[];
+    float* Ms = sm;                    // [DP][DP+1]   Ms[i][j]
+    float* Ls = sm + DP * (DP + 1);    // [TT][DP+1]
+    const int d = p + dk;
+    const int bh = blockIdx.y, b = bh / H, h = bh % H;
+    const int t0 = blockIdx.x * TT;
+    const int nt = min(TT, n - t0);
+    const float* M = Mat + (long long)bh * d * d;
+    for (int e = threadIdx.x; e < DP * DP; e += 256) {
+        int i = e / DP, j = e % DP;
+        float v = 0.f;
+        if (i < d && j < d) v = transM ? M[j * d + i] : M[i * d + j];
+        Ms[i * (DP + 1) + j] = v;
+    }
+    for (int e = threadIdx.x; e < TT * DP; e += 256) {
+        int r = e / DP, i = e % DP;
+        float v = 0.f;
+        if (r < nt && i < d) v = load_aug(L, pos, p, dk, h, (long long)b * n + t0 + r, i);
+        Ls[r * (DP + 1) + i] = v;
+    }
+    __syncthreads();
+    const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
+    float acc[4][MT];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < MT; ++c) acc[a][c] = 0.f;
+    for (int i = 0; i < d; ++i) {
+        float lv[4], mv[MT];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) lv[a] = Ls[(ty + 16 * a) * (DP + 1) + i];
+#pragma unroll
+        for (int c = 0; c < MT; ++c) mv[c] = Ms[i * (DP + 1) + tx + 16 * c];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < MT; ++c) acc[a][c] = fmaf(lv[a], mv[c], acc[a][c]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        int r = ty + 16 * a;
+        if (r >= nt) continue;
+        long long t = (long long)b * n + t0 + r;
+#pragma unroll
+        for (int c = 0; c < MT; ++c) {
+            int j = tx + 16 * c;
+            if (j >= d) continue;
+            float v = acc[a][c] * oscale;
+            if (out_augmented) out[t * ldo + ocol0 + h * d + j] = v;
+            else if (j >= p) out[t * ldo + ocol0 + h * dk + (j - p)] = v;
+        }
+    }
+}
+
+static int pick_dp(int d) { return d <= 32 ? 32 : d <= 64 ? 64 : d <= 128 ? 128 : 0; }
+
+}  // namespace gb200
+
+using namespace gb200;
+
+static HeadOperand make_op(const gb200_head_operand* o) {
+    HeadOperand h;
+    h.ptr = o->ptr; h.ld = o->ld; h.col0 = o->col0; h.augmented = o->augmented;
+    h.gamma = o->gamma; h.beta = o->beta;
+    return h;
+}
+
+extern "C" int gb200_headnorm_fwd(int device, float* x, int ld, int col0, long long T, int H, int dk, float eps,
+                                  float* rstd, void* stream) {
+    use_device(device);
+    GB_REQUIRE(x && rstd && T >= 0 && H >= 1 && dk >= 1, "gb200_headnorm_fwd: bad arguments");
+    if (T == 0) return GB200_OK;
+    size_t smem = (size_t)HN_ROWS * (H * dk + 1) * sizeof(float);
+    GB_REQUIRE(smem <= 200 * 1024, "gb200_headnorm_fwd: H*d_k=%d too wide", H * dk);
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(headnorm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    headnorm_fwd_kernel<<<cdiv(T, HN_ROWS), 256, smem, as_stream(stream)>>>(x, ld, col0, T, H, dk, eps, rstd);
+    return check_launch("gb200_headnorm_fwd");
+}
+
+extern "C" size_t gb200_headnorm_bwd_workspace_bytes(long long T, int H, int dk) {
+    return (size_t)cdiv(T, HN_ROWS) * 2 * H * dk * sizeof(float);
+}
+
+extern "C" int gb200_headnorm_bwd(int device, float* dy, int lddy, int dcol0, const float* xhat, int ldx,
+                                  int xcol0, const float* rstd, const float* gamma, long long T, int H, int dk,
+                                  float* dgamma, float* dbeta, int accumulate, float* workspace,
+                                  size_t workspace_bytes, void* stream) {
+    use_device(device);
+    GB_REQUIRE(dy && xhat && rstd && gamma && dgamma && dbeta, "gb200_headnorm_bwd: null argument");
+    if (T == 0) return GB200_OK;
+    GB_REQUIRE(workspace && workspace_bytes >= gb200_headnorm_bwd_workspace_bytes(T, H, dk),
+               "gb200_headnorm_bwd: workspace too small");
+    size_t smem = (size_t)2 * HN_ROWS * (H * dk + 1) * sizeof(float);
+    GB_REQUIRE(smem <= 200 * 1024, "gb200_headnorm_bwd: H*d_k=%d too wide", H * dk);
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(headnorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int nblocks = cdiv(T, HN_ROWS);
+    cudaStream_t st = as_stream(stream);
+    headnorm_bwd_kernel<<<nblocks, 256, smem, st>>>(dy, lddy, dcol0, xhat, ldx, xcol0, rstd, gamma, T, H, dk,
+                                                   workspace);
+    headnorm_bwd_reduce_kernel<<<cdiv(H * dk, 128), 128, 0, st>>>(workspace, nblocks, H * dk, dgamma, dbeta,
+                                                                 accumulate);
+    return check_launch("gb200_headnorm_bwd", 2);
+}
+
+extern "C" int gb200_attn_suggest_nsplit(int B, int H, int n) {
+    int bh = B * H;
+    int want = (3 * 148 + bh - 1) / bh;
+    int maxs = (n + 63) / 64;
+    int s = want < maxs ? want : maxs;
+    return s < 1 ? 1 : s;
+}
+
+extern "C" size_t gb200_attn_xty_workspace_bytes(int B, int H, int d, int nsplit) {
+    return (size_t)B * H * nsplit * d * d * sizeof(float);
+}
+
+extern "C" int gb200_attn_xty(int device, const gb200_head_operand* L, const gb200_head_operand* R,
+                              const float* pos, int B, int H, int n, int dk, int p, float scale,
+                              const unsigned char* keep_mask, float* out, int nsplit, float* workspace,
+                              size_t workspace_bytes, void* stream) {
+    use_device(device);
+    GB_REQUIRE(L && R && out && L->ptr && R->ptr, "gb200_attn_xty: null operand");
+    GB_REQUIRE(B >= 1 && H >= 1 && n >= 1 && dk >= 1 && p >= 0, "gb200_attn_xty: bad shape");
+    GB_REQUIRE(p == 0 || pos || (L->augmented && R->augmented), "gb200_attn_xty: pos is null but pos_dim=%d", p);
+    const int d = dk + p, dp = pick_dp(d);
+    GB_REQUIRE(dp != 0, "gb200_attn_xty: head width d_k+pos_dim=%d > 128 unsupported", d);
+    if (nsplit < 1) nsplit = 1;
+    GB_REQUIRE(workspace && workspace_bytes >= gb200_attn_xty_workspace_bytes(B, H, d, nsplit),
+               "gb200_attn_xty: workspace too small");
+    GB_REQUIRE(B * H <= 65535, "gb200_attn_xty: B*H too large");
+    const int chunk = cdiv(n, nsplit);
+    dim3 grid(nsplit, B * H);
+    cudaStream_t st = as_stream(stream);
+    HeadOperand l = make_op(L), r = make_op(R);
+    if (dp == 32) xty_kernel<32><<<grid, 256, 0, st>>>(l, r, pos, p, dk, H, n, nsplit, chunk, workspace);
+    else if (dp == 64) xty_kernel<64><<<grid, 256, 0, st>>>(l, r, pos, p, dk, H, n, nsplit, chunk, workspace);
+    else xty_kernel<128><<<grid, 256, 0, st>>>(l, r, pos, p, dk, H, n, nsplit, chunk, workspace);
+    long long total = (long long)B * H * d * d;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    xty_reduce_kernel<<<blocks, 256, 0, st>>>(workspace, nsplit, d * d, total, scale, keep_mask, out);
+    return check_launch("gb200_attn_xty", 2);
+}
+
+extern "C" int gb200_attn_xm(int device, const gb200_head_operand* L, const float* pos, const float* M,
+                             int transM, int B, int H, int n, int dk, int p, float* out, int ldo, int ocol0,
+                             int out_augmented, float out_scale, void* stream) {
+    use_device(device);
+    GB_REQUIRE(L && L->ptr && M && out, "gb200_attn_xm: null operand");
+    GB_REQUIRE(p == 0 || pos || L->augmented, "gb200_attn_xm: pos is null but pos_dim=%d", p);
+    const int d = dk + p, dp = pick_dp(d);
+    GB_REQUIRE(dp != 0, "gb200_attn_xm: head width d_k+pos_dim=%d > 128 unsupported", d);
+    GB_REQUIRE(B * H <= 65535, "gb200_attn_xm: B*H too large");
+    dim3 grid(cdiv(n, 64), B * H);
+    size_t smem = (size_t)(dp + 64) * (dp + 1) * sizeof(float);
+    cudaStream_t st = as_stream(stream);
+    HeadOperand l = make_op(L);
+#define LAUNCH_XM(DPV)                                                                                  \
+    do {                                                                                                \
+        if (smem > 48 * 1024)                                                                           \
+            cudaFuncSetAttribute(xm_kernel<DPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        xm_kernel<DPV><<<grid, 256, smem, st>>>(l, pos, M, transM, p, dk, H, n, out, ldo, ocol0,          \
+                                               out_augmented, out_scale);                               \
+    } while (0)
+    if (dp == 32) LAUNCH_XM(32);
+    else if (dp == 64) LAUNCH_XM(64);
+    else LAUNCH_XM(128);
+#undef LAUNCH_XM
+    return check_launch("gb200_attn_xm");
+}

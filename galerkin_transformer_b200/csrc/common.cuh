@@ -1,0 +1,81 @@
+// Shared device/host helpers for libgalerkin_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/galerkin_b200.h"
+
+namespace gb200 {
+
+// ---- error plumbing: C entry points return 0 / non-zero and keep a thread-local message ----
+void set_error(const char* fmt, ...);
+int check_launch(const char* what, int nkernels = 1);  // cudaGetLastError -> error string; counts launches
+void use_device(int device);                 // thread-local cached cudaSetDevice
+
+#define GB_REQUIRE(cond, ...)                                  \
+    do {                                                       \
+        if (!(cond)) {                                         \
+            gb200::set_error(__VA_ARGS__);                     \
+            return GB200_ERR_INVALID;                          \
+        }                                                      \
+    } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- activations --------------------------------------------------------------------------
+enum { ACT_NONE = GB200_ACT_NONE, ACT_RELU = GB200_ACT_RELU, ACT_SILU = GB200_ACT_SILU };
+
+__device__ __forceinline__ float act_apply(int act, float v) {
+    if (act == ACT_RELU) return v > 0.f ? v : 0.f;
+    if (act == ACT_SILU) return v / (1.f + __expf(-v));
+    return v;
+}
+// derivative w.r.t. the pre-activation z
+__device__ __forceinline__ float act_grad(int act, float z) {
+    if (act == ACT_RELU) return z > 0.f ? 1.f : 0.f;
+    if (act == ACT_SILU) {
+        float s = 1.f / (1.f + __expf(-z));
+        return s * (1.f + z * (1.f - s));
+    }
+    return 1.f;
+}
+
+// ---- counter-based RNG for fused dropout: Philox4x32-10 keyed by (seed, element index) -----
+// The same (seed, index) reproduces the same keep decision in forward and backward, so no
+// mask tensor ever touches HBM.
+__device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+
+__device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t idx) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    uint32_t c0 = (uint32_t)idx, c1 = (uint32_t)(idx >> 32), c2 = 0x9E3779B9u, c3 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+        uint32_t h0 = mulhi32(M0, c0), l0 = M0 * c0;
+        uint32_t h1 = mulhi32(M1, c2), l1 = M1 * c2;
+        uint32_t n0 = h1 ^ c1 ^ k0, n1 = l1, n2 = h0 ^ c3 ^ k1, n3 = l0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+// keep-scale for element `idx`: 0 if dropped, 1/(1-p) if kept.  p in [0,1).
+__device__ __forceinline__ float dropout_scale(float p, uint64_t seed, uint64_t idx) {
+    if (p <= 0.f) return 1.f;
+    uint4 r = philox4x32(seed, idx >> 2);
+    uint32_t u = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
+    float uf = (float)(u >> 8) * (1.0f / 16777216.0f);       // [0,1)
+    return uf < p ? 0.f : 1.f / (1.f - p);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace gb200

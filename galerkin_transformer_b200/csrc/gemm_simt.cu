@@ -1,0 +1,312 @@
+// Exact-fp32 SIMT GEMM with a fused epilogue (bias, activation, Philox dropout, signed
+// residual, pre-activation side output) and deterministic split-K.
+//
+// This is the precise path of the library (fp32 FMA, no TF32 rounding): it serves the
+// contractions whose shapes do not fit a tcgen05 tile (K = 2 grid columns, N = 1 output
+// head, weight-gradient reductions over tokens) and is the on-device cross-check for the
+// tensor-core GEMM in gemm_tc.cu.
+//
+//   C[b] = R[b] + rscale * drop( act( alpha * op(A[b]) . op(B[b]) + bias ) )      (+= if accumulate)
+//
+// Replaces, on the reference side, every nn.Linear / torch.matmul on the hot path:
+// libs/layers.py:837-839 (Q,K,V projections), :896-897 (fc), :980-986 (FeedForward),
+// :1083/:1172 (SpectralConv residual Linear) and libs/model.py:615-617, 629 (regressor).
+#include "common.cuh"
+
+namespace gb200 {
+
+constexpr int BM = 64, BN = 64, BK = 16, PAD = 4, NT = 256;
+
+struct GemmArgs {
+    const float* A; const float* B; float* C;
+    int M, N, K, lda, ldb, ldc;
+    long long sA, sB, sC;
+    int nbatch, ksplit, kchunk;
+    float alpha;
+    const float* bias;
+    int act;
+    float* Z; int ldz;
+    float drop_p; unsigned long long seed;
+    const float* R; int ldr; float rscale;
+    int accumulate;
+    float* ws;
+    int vecA, vecB;
+};
+
+__device__ __forceinline__ void epilogue_store(const GemmArgs& g, int batch, int m, int n, float acc) {
+    float v = g.alpha * acc;
+    if (g.bias) v += g.bias[n];
+    if (g.Z) g.Z[(long long)batch * g.sC + (long long)m * g.ldz + n] = v;
+    v = act_apply(g.act, v);
+    if (g.drop_p > 0.f)
+        v *= dropout_scale(g.drop_p, g.seed, ((unsigned long long)batch * g.M + m) * g.N + n);
+    float* c = g.C + (long long)batch * g.sC + (long long)m * g.ldc + n;
+    if (g.R) v = g.R[(long long)batch * g.sC + (long long)m * g.ldr + n] + g.rscale * v;
+    else v *= g.rscale;
+    if (g.accumulate) v += *c;
+    *c = v;
+}
+
+// 4 consecutive elements along the contiguous storage dimension, zero-filled out of range.
+__device__ __forceinline__ float4 load4(const float* base, long long row, int ld, int col, int nrows,
+                                        int ncols, bool vec) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row >= nrows) return v;
+    const float* p = base + row * ld + col;
+    if (vec && col + 3 < ncols) return *reinterpret_cast<const float4*>(p);
+    if (col + 0 < ncols) v.x = p[0];
+    if (col + 1 < ncols) v.y = p[1];
+    if (col + 2 < ncols) v.z = p[2];
+    if (col + 3 < ncols) v.w = p[3];
+    return v;
+}
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmArgs g) {
+    __shared__ __align__(16) float As[2][BK][BM + PAD];
+    __shared__ __align__(16) float Bs[2][BK][BN + PAD];
+    const int tid = threadIdx.x;
+    const int batch = blockIdx.z / g.ksplit, split = blockIdx.z % g.ksplit;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const float* A = g.A + (long long)batch * g.sA;
+    const float* B = g.B + (long long)batch * g.sB;
+    const int kbeg = split * g.kchunk;
+    const int kend = min(g.K, kbeg + g.kchunk);
+    const int nkt = (kend - kbeg + BK - 1) / BK;
+
+    float4 ra, rb;
+    auto gload = [&](int kt) {
+        const int k0 = kbeg + kt * BK;
+        if (!TA) ra = load4(A, m0 + tid / 4, g.lda, k0 + (tid % 4) * 4, g.M, kend, g.vecA);
+        else     ra = load4(A, k0 + tid / 16, g.lda, m0 + (tid % 16) * 4, kend, g.M, g.vecA);
+        if (!TB) rb = load4(B, k0 + tid / 16, g.ldb, n0 + (tid % 16) * 4, kend, g.N, g.vecB);
+        else     rb = load4(B, n0 + tid / 4, g.ldb, k0 + (tid % 4) * 4, g.N, kend, g.vecB);
+    };
+    auto sstore = [&](int buf) {
+        if (!TA) {
+            int r = tid / 4, kq = (tid % 4) * 4;
+            As[buf][kq + 0][r] = ra.x; As[buf][kq + 1][r] = ra.y;
+            As[buf][kq + 2][r] = ra.z; As[buf][kq + 3][r] = ra.w;
+        } else {
+            *reinterpret_cast<float4*>(&As[buf][tid / 16][(tid % 16) * 4]) = ra;
+        }
+        if (!TB) {
+            *reinterpret_cast<float4*>(&Bs[buf][tid / 16][(tid % 16) * 4]) = rb;
+        } else {
+            int r = tid / 4, kq = (tid % 4) * 4;
+            Bs[buf][kq + 0][r] = rb.x; Bs[buf][kq + 1][r] = rb.y;
+            Bs[buf][kq + 2][r] = rb.z; Bs[buf][kq + 3][r] = rb.w;
+        }
+    };
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const int ty = tid / 16, tx = tid % 16;
+    if (nkt > 0) {
+        gload(0);
+        sstore(0);
+    }
+    __syncthreads();
+    for (int kt = 0; kt < nkt; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nkt) gload(kt + 1);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+            float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (kt + 1 < nkt) sstore(buf ^ 1);
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= g.N) continue;
+            if (g.ksplit > 1)
+                g.ws[(((long long)batch * g.ksplit + split) * g.M + m) * g.N + n] = acc[i][j];
+            else
+                epilogue_store(g, batch, m, n, acc[i][j]);
+        }
+    }
+}
+
+// fixed-order sum of the split-K partials followed by the epilogue (run-to-run deterministic)
+__global__ void splitk_reduce_kernel(GemmArgs g) {
+    const long long total = (long long)g.nbatch * g.M * g.N;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(e % g.N);
+        const int m = (int)((e / g.N) % g.M);
+        const int batch = (int)(e / ((long long)g.M * g.N));
+        float s = 0.f;
+        const float* p = g.ws + ((long long)batch * g.ksplit * g.M + m) * g.N + n;
+        for (int k = 0; k < g.ksplit; ++k) s += p[(long long)k * g.M * g.N];
+        epilogue_store(g, batch, m, n, s);
+    }
+}
+
+// column sums of a row-major [M,N] matrix (bias gradients), two deterministic stages
+__global__ void colsum_partial_kernel(const float* __restrict__ X, int M, int N, int ld,
+                                      int rows_per_block, float* __restrict__ part) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r0 = blockIdx.y * rows_per_block;
+    const int r1 = min(M, r0 + rows_per_block);
+    __shared__ float red[8][33];
+    float s = 0.f;
+    if (n < N)
+        for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) s += X[(long long)r * ld + n];
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && n < N) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+        part[(long long)blockIdx.y * N + n] = t;
+    }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ part, int nparts, int N, float scale,
+                                    int accumulate, float* __restrict__ out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += part[(long long)p * N + n];
+    s *= scale;
+    out[n] = accumulate ? out[n] + s : s;
+}
+
+// g = dy * rscale * dropmask * act'(z)   (backward of the GEMM epilogue, elementwise)
+__global__ void epilogue_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ z,
+                                    int ldz, const float* __restrict__ y, int ldy, float* __restrict__ gout,
+                                    int ldg, long long M, int N, int act, float rscale, float drop_p,
+                                    unsigned long long seed) {
+    const long long total = M * N;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long m = e / N;
+        const int n = (int)(e % N);
+        float v = dy[m * lddy + n] * rscale;
+        if (drop_p > 0.f) v *= dropout_scale(drop_p, seed, (unsigned long long)e);
+        if (act == ACT_RELU) {
+            // relu'(z) from the stored output: y > 0 <=> z > 0 and kept (dropped => v already 0)
+            float ref = z ? z[m * ldz + n] : y[m * ldy + n];
+            v = ref > 0.f ? v : 0.f;
+        } else if (act == ACT_SILU) {
+            v *= act_grad(ACT_SILU, z[m * ldz + n]);
+        }
+        gout[m * ldg + n] = v;
+    }
+}
+
+}  // namespace gb200
+
+using namespace gb200;
+
+extern "C" size_t gb200_gemm_workspace_bytes(int M, int N, int K, int nbatch, int ksplit) {
+    (void)K;
+    return ksplit > 1 ? (size_t)nbatch * ksplit * M * N * sizeof(float) : 0;
+}
+
+extern "C" int gb200_gemm_suggest_ksplit(int M, int N, int K, int nbatch) {
+    long long tiles = (long long)cdiv(M, BM) * cdiv(N, BN) * nbatch;
+    if (tiles >= 148 || K < 512) return 1;
+    int want = (int)((2 * 148 + tiles - 1) / tiles);
+    int maxs = K / 256;
+    if (maxs < 1) maxs = 1;
+    int s = want < maxs ? want : maxs;
+    return s < 1 ? 1 : (s > 128 ? 128 : s);
+}
+
+extern "C" int gb200_gemm(int device, const float* A, int lda, int transA, const float* B, int ldb,
+                          int transB, float* C, int ldc, int M, int N, int K, int nbatch,
+                          long long strideA, long long strideB, long long strideC, float alpha,
+                          const float* bias, int act, float* Zout, int ldz, float drop_p,
+                          unsigned long long seed, const float* R, int ldr, float rscale,
+                          int accumulate, int ksplit, float* workspace, size_t workspace_bytes,
+                          void* stream) {
+    use_device(device);
+    GB_REQUIRE(M >= 0 && N >= 0 && K >= 0 && nbatch >= 1, "gb200_gemm: bad shape M=%d N=%d K=%d nb=%d", M, N, K, nbatch);
+    if (M == 0 || N == 0) return GB200_OK;
+    GB_REQUIRE(A && B && C, "gb200_gemm: null operand");
+    GB_REQUIRE(act == ACT_NONE || act == ACT_RELU || act == ACT_SILU, "gb200_gemm: unknown activation %d", act);
+    GB_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "gb200_gemm: dropout p=%f outside [0,1)", drop_p);
+    if (ksplit < 1) ksplit = 1;
+    if (K == 0) ksplit = 1;
+    GemmArgs g;
+    g.A = A; g.B = B; g.C = C; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+    g.sA = strideA; g.sB = strideB; g.sC = strideC; g.nbatch = nbatch; g.ksplit = ksplit;
+    int ktiles = cdiv(K > 0 ? K : 1, BK);
+    g.kchunk = cdiv(ktiles, ksplit) * BK;
+    g.alpha = alpha; g.bias = bias; g.act = act; g.Z = Zout; g.ldz = ldz; g.drop_p = drop_p;
+    g.seed = seed; g.R = R; g.ldr = ldr; g.rscale = rscale; g.accumulate = accumulate;
+    g.ws = workspace;
+    g.vecA = ((uintptr_t)A % 16 == 0) && (lda % 4 == 0) && (strideA % 4 == 0);
+    g.vecB = ((uintptr_t)B % 16 == 0) && (ldb % 4 == 0) && (strideB % 4 == 0);
+    if (ksplit > 1)
+        GB_REQUIRE(workspace && workspace_bytes >= gb200_gemm_workspace_bytes(M, N, K, nbatch, ksplit),
+                   "gb200_gemm: split-K workspace too small (%zu bytes)", workspace_bytes);
+    dim3 grid(cdiv(N, BN), cdiv(M, BM), nbatch * ksplit);
+    GB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gb200_gemm: grid too large");
+    cudaStream_t st = as_stream(stream);
+    if (!transA && !transB) gemm_simt_kernel<false, false><<<grid, NT, 0, st>>>(g);
+    else if (!transA && transB) gemm_simt_kernel<false, true><<<grid, NT, 0, st>>>(g);
+    else if (transA && !transB) gemm_simt_kernel<true, false><<<grid, NT, 0, st>>>(g);
+    else gemm_simt_kernel<true, true><<<grid, NT, 0, st>>>(g);
+    if (ksplit > 1) {
+        long long total = (long long)nbatch * M * N;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        splitk_reduce_kernel<<<blocks, 256, 0, st>>>(g);
+    }
+    return check_launch("gb200_gemm", ksplit > 1 ? 2 : 1);
+}
+
+extern "C" size_t gb200_colsum_workspace_bytes(long long M, int N) {
+    int rows_per_block = 256;
+    return (size_t)cdiv(M, rows_per_block) * N * sizeof(float);
+}
+
+extern "C" int gb200_colsum(int device, const float* X, int ld, long long M, int N, float scale,
+                            int accumulate, float* out, float* workspace, size_t workspace_bytes,
+                            void* stream) {
+    use_device(device);
+    GB_REQUIRE(X && out && M >= 1 && N >= 1, "gb200_colsum: bad arguments");
+    const int rows_per_block = 256;
+    int nparts = cdiv(M, rows_per_block);
+    GB_REQUIRE(workspace && workspace_bytes >= (size_t)nparts * N * sizeof(float),
+               "gb200_colsum: workspace too small");
+    GB_REQUIRE(nparts <= 65535, "gb200_colsum: too many rows");
+    cudaStream_t st = as_stream(stream);
+    colsum_partial_kernel<<<dim3(cdiv(N, 32), nparts), dim3(32, 8), 0, st>>>(X, (int)M, N, ld, rows_per_block,
+                                                                               workspace);
+    colsum_final_kernel<<<cdiv(N, 128), 128, 0, st>>>(workspace, nparts, N, scale, accumulate, out);
+    return check_launch("gb200_colsum", 2);
+}
+
+extern "C" int gb200_epilogue_bwd(int device, const float* dy, int lddy, const float* z, int ldz,
+                                  const float* y, int ldy, float* g, int ldg, long long M, int N, int act,
+                                  float rscale, float drop_p, unsigned long long seed, void* stream) {
+    use_device(device);
+    GB_REQUIRE(dy && g && M >= 0 && N >= 1, "gb200_epilogue_bwd: bad arguments");
+    GB_REQUIRE(act != ACT_SILU || z, "gb200_epilogue_bwd: SiLU backward needs the pre-activation");
+    GB_REQUIRE(act != ACT_RELU || z || y, "gb200_epilogue_bwd: ReLU backward needs z or y");
+    if (M == 0) return GB200_OK;
+    long long total = M * N;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    epilogue_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(dy, lddy, z, ldz, y, ldy, g, ldg, M, N, act,
+                                                               rscale, drop_p, seed);
+    return check_launch("gb200_epilogue_bwd");
+}

@@ -1,0 +1,573 @@
+"""Autograd functions over the C ABI (include/galerkin_b200.h).
+
+Every function here hands raw device pointers, sizes and the current CUDA stream to
+libgalerkin_b200.so; PyTorch is used for memory (torch.empty from the caching allocator),
+streams and the autograd graph only.  Backward runs on PyTorch's autograd thread; the
+library is re-entrant and takes the device ordinal on every call.
+"""
+import math
+import threading
+
+import torch
+
+from . import _lib
+from ._lib import HeadOperand, check, ptr, stream_of, workspace, require_cuda_f32
+
+ACT = {"none": 0, None: 0, "identity": 0, "relu": 1, "silu": 2}
+
+_seed_lock = threading.Lock()
+_seed_counter = 0
+
+
+def next_seed():
+    """64-bit Philox key for one fused-dropout site: derived from torch's seed and a call counter
+    (deterministic under torch.manual_seed, distinct per call and per rank)."""
+    global _seed_counter
+    with _seed_lock:
+        _seed_counter += 1
+        c = _seed_counter
+    return (torch.initial_seed() * 0x9E3779B97F4A7C15 + c * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
+
+
+def _dev(t):
+    return t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+
+class Profiler:
+    """Optional per-launch CUDA-event attribution (bench.py's roofline pass).  When enabled every
+    native launch is bracketed by two events on the launching stream and tagged with its
+    ALGORITHMIC flops / bytes."""
+    enabled = False
+    records = []          # (family, start_event, end_event, flops, bytes)
+
+    @classmethod
+    def reset(cls):
+        cls.records = []
+
+    @classmethod
+    def summary(cls):
+        agg = {}
+        for fam, s, e, fl, by in cls.records:
+            a = agg.setdefault(fam, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+            a["launches"] += 1
+            a["ms"] += s.elapsed_time(e)
+            a["flops"] += fl
+            a["bytes"] += by
+        return agg
+
+
+def _launch(family, flops, nbytes, fn, *args):
+    if Profiler.enabled:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = fn(*args)
+        e.record()
+        Profiler.records.append((family, s, e, float(flops), float(nbytes)))
+    else:
+        rc = fn(*args)
+    if rc != 0:
+        check(rc, family)
+
+
+# ------------------------------------------------------------------------------------------
+# raw launches
+# ------------------------------------------------------------------------------------------
+def gemm(A, B, C, M, N, K, *, lda, ldb, ldc, transA=False, transB=False, alpha=1.0, bias=None, act=0,
+         zout=None, ldz=0, drop_p=0.0, seed=0, residual=None, ldr=0, rscale=1.0, accumulate=False,
+         ksplit=None, a_off=0, b_off=0, c_off=0):
+    """C = R + rscale*drop(act(alpha*op(A).op(B)+bias)); offsets are in floats."""
+    lib = _lib.load()
+    if ksplit is None:
+        ksplit = lib.gb200_gemm_suggest_ksplit(M, N, K, 1)
+    ws_bytes = lib.gb200_gemm_workspace_bytes(M, N, K, 1, ksplit)
+    ws = workspace(ws_bytes, C)
+    fam = "gemm_" + ("t" if transA else "n") + ("t" if transB else "n")
+    nbytes = 4.0 * (M * K + K * N + M * N * (1 + (residual is not None) + (zout is not None)))
+    _launch(fam, 2.0 * M * N * K, nbytes, lib.gb200_gemm, _dev(C), ptr(A) + 4 * a_off, lda, int(transA),
+            ptr(B) + 4 * b_off, ldb, int(transB), ptr(C) + 4 * c_off, ldc, M, N, K, 1, 0, 0, 0, alpha, ptr(bias),
+            act, ptr(zout), ldz, drop_p, seed, ptr(residual), ldr, rscale, int(accumulate), ksplit, ptr(ws),
+            ws_bytes, stream_of(C))
+
+
+def colsum(X, M, N, ld, out, *, x_off=0, scale=1.0, accumulate=False):
+    lib = _lib.load()
+    ws_bytes = lib.gb200_colsum_workspace_bytes(M, N)
+    ws = workspace(ws_bytes, X)
+    _launch("colsum", M * N, 4.0 * M * N, lib.gb200_colsum, _dev(X), ptr(X) + 4 * x_off, ld, M, N, scale,
+            int(accumulate), ptr(out), ptr(ws), ws_bytes, stream_of(X))
+
+
+def epilogue_bwd(dy, M, N, *, z=None, y=None, act=0, rscale=1.0, drop_p=0.0, seed=0):
+    g = torch.empty((M, N), dtype=torch.float32, device=dy.device)
+    _launch("epilogue_bwd", 4.0 * M * N, 4.0 * M * N * (2 + (act != 0)), _lib.load().gb200_epilogue_bwd,
+            _dev(dy), ptr(dy), N, ptr(z), N, ptr(y), N, ptr(g), N, M, N, act, rscale, drop_p, seed,
+            stream_of(dy))
+    return g
+
+
+# ------------------------------------------------------------------------------------------
+# Linear (+bias, activation, fused dropout, signed residual)
+# ------------------------------------------------------------------------------------------
+class _LinearFn(torch.autograd.Function):
+    """y = residual + rscale * dropout_p(act(x @ W^T + b));  x: (M, K), W: (N, K)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, act, rscale, drop_p, seed):
+        require_cuda_f32(x, weight, bias, residual)
+        M, K = x.shape
+        N = weight.shape[0]
+        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        need_z = act == ACT["silu"] and (x.requires_grad or weight.requires_grad)
+        z = torch.empty_like(y) if need_z else None
+        gemm(x, weight, y, M, N, K, lda=K, ldb=K, ldc=N, transB=True, bias=bias, act=act, zout=z, ldz=N,
+             drop_p=drop_p, seed=seed, residual=residual, ldr=N, rscale=rscale)
+        ctx.save_for_backward(x, weight, z, y if act == ACT["relu"] else None)
+        ctx.cfg = (act, rscale, drop_p, seed, bias is not None, residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, z, y = ctx.saved_tensors
+        act, rscale, drop_p, seed, has_bias, has_res = ctx.cfg
+        dy = dy.contiguous()
+        M, K = x.shape
+        N = weight.shape[0]
+        if act != 0 or drop_p > 0.0 or rscale != 1.0:
+            g = epilogue_bwd(dy, M, N, z=z, y=y, act=act, rscale=rscale, drop_p=drop_p, seed=seed)
+        else:
+            g = dy
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            gemm(g, weight, dx, M, K, N, lda=N, ldb=K, ldc=K)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(weight)
+            gemm(g, x, dw, N, K, M, lda=N, ldb=K, ldc=K, transA=True)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = torch.empty(N, dtype=torch.float32, device=x.device)
+            colsum(g, M, N, N, db)
+        dres = dy if (has_res and ctx.needs_input_grad[3]) else None
+        return dx, dw, db, dres, None, None, None, None
+
+
+def linear(x, weight, bias=None, *, act="none", residual=None, rscale=1.0, drop_p=0.0):
+    """nn.Linear over the last dimension with the fused epilogue; any leading shape."""
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1]).contiguous()
+    r2 = None if residual is None else residual.reshape(-1, weight.shape[0]).contiguous()
+    seed = next_seed() if drop_p > 0.0 else 0
+    y = _LinearFn.apply(x2, weight, bias, r2, ACT[act], float(rscale), float(drop_p), seed)
+    return y.reshape(*lead, weight.shape[0])
+
+
+class _LinearCatFn(torch.autograd.Function):
+    """y = [x1 | x2] @ W^T + b without materialising the concatenation
+    (torch.cat([x, grid], -1) -> fc, libs/model.py:615-617)."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, weight, bias):
+        require_cuda_f32(x1, x2, weight, bias)
+        M, K1 = x1.shape
+        K2 = x2.shape[1]
+        N, K = weight.shape
+        assert K == K1 + K2
+        y = torch.empty((M, N), dtype=torch.float32, device=x1.device)
+        gemm(x1, weight, y, M, N, K1, lda=K1, ldb=K, ldc=N, transB=True, bias=bias)
+        gemm(x2, weight, y, M, N, K2, lda=K2, ldb=K, ldc=N, transB=True, accumulate=True, b_off=K1)
+        ctx.save_for_backward(x1, x2, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x1, x2, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        M, K1 = x1.shape
+        K2 = x2.shape[1]
+        N, K = weight.shape
+        dx1 = dx2 = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx1 = torch.empty_like(x1)
+            gemm(dy, weight, dx1, M, K1, N, lda=N, ldb=K, ldc=K1)
+        if ctx.needs_input_grad[1]:
+            dx2 = torch.empty_like(x2)
+            gemm(dy, weight, dx2, M, K2, N, lda=N, ldb=K, ldc=K2, b_off=K1)
+        if ctx.needs_input_grad[2]:
+            dw = torch.empty_like(weight)
+            gemm(dy, x1, dw, N, K1, M, lda=N, ldb=K1, ldc=K, transA=True)
+            gemm(dy, x2, dw, N, K2, M, lda=N, ldb=K2, ldc=K, transA=True, c_off=K1)
+        if ctx.has_bias and ctx.needs_input_grad[3]:
+            db = torch.empty(N, dtype=torch.float32, device=dy.device)
+            colsum(dy, M, N, N, db)
+        return dx1, dx2, dw, db
+
+
+def linear_cat(x1, x2, weight, bias=None):
+    lead = x1.shape[:-1]
+    y = _LinearCatFn.apply(x1.reshape(-1, x1.shape[-1]).contiguous(),
+                           x2.reshape(-1, x2.shape[-1]).contiguous(), weight, bias)
+    return y.reshape(*lead, weight.shape[0])
+
+
+# ------------------------------------------------------------------------------------------
+# Row LayerNorm
+# ------------------------------------------------------------------------------------------
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        require_cuda_f32(x, gamma, beta)
+        rows, width = x.shape
+        y = torch.empty_like(x)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        _launch("layernorm_fwd", 8.0 * rows * width, 8.0 * rows * width, _lib.load().gb200_layernorm_fwd,
+                _dev(x), ptr(x), rows, width, ptr(gamma), ptr(beta), eps, ptr(y), ptr(mean), ptr(rstd),
+                stream_of(x))
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        dy = dy.contiguous()
+        rows, width = x.shape
+        lib = _lib.load()
+        dx = torch.empty_like(x)
+        dg = torch.empty_like(gamma)
+        db = torch.empty_like(gamma)
+        ws_bytes = lib.gb200_layernorm_bwd_workspace_bytes(rows, width)
+        ws = workspace(ws_bytes, x)
+        _launch("layernorm_bwd", 14.0 * rows * width, 12.0 * rows * width, lib.gb200_layernorm_bwd, _dev(x),
+                ptr(dy), ptr(x), ptr(mean), ptr(rstd), ptr(gamma), rows, width, ptr(dx), ptr(dg), ptr(db), 0,
+                ptr(ws), ws_bytes, stream_of(x))
+        return dx, dg, db, None
+
+
+def layer_norm(x, gamma, beta, eps):
+    shape = x.shape
+    return _LayerNormFn.apply(x.reshape(-1, shape[-1]).contiguous(), gamma, beta, float(eps)).reshape(shape)
+
+
+# ------------------------------------------------------------------------------------------
+# Attention: Q/K/V projection + per-head LayerNorm + position columns + K^T V + Q.(.)
+# ------------------------------------------------------------------------------------------
+def _hop(t, ld, col0, augmented=False, gamma=None, beta=None):
+    return HeadOperand(ptr(t), ld, col0, int(augmented), ptr(gamma), ptr(beta))
+
+
+class _LinearAttentionFn(torch.autograd.Function):
+    """(query, key, value) -> head-merged attention output (B, n, H*(p+dk)) and A (B,H,d,d).
+
+    Galerkin  (libs/layers.py:708-734):  A = mask2 * K~^T V~ / n,           out = Q~ A
+    Fourier in linear form (exact reassociation of libs/layers.py:687-703 when the n x n
+    dropout is off):                     A = K~^T V~ / (sqrt(d) n),          out = Q~ A
+    with ~ = [pos | per-head-LayerNorm(.)] on the operands selected by `norm_on`.
+    """
+
+    @staticmethod
+    def forward(ctx, query, key, value, pos, wqkv, bqkv, g1, b1, g2, b2, keep_mask, cfg):
+        H, dk, p, eps, norm_on, scale, self_attn = cfg
+        require_cuda_f32(query, key, value, pos, wqkv, bqkv, g1, b1, g2, b2)
+        lib = _lib.load()
+        B, n, dm = query.shape
+        T, d = B * n, dk + p
+        dev = _dev(query)
+        st = stream_of(query)
+        qkv = torch.empty((T, 3 * dm), dtype=torch.float32, device=query.device)
+        xs = [t.reshape(T, dm) for t in (query, key, value)]
+        if self_attn:      # one GEMM, N = 3*d_model
+            gemm(xs[0], wqkv, qkv, T, 3 * dm, dm, lda=dm, ldb=dm, ldc=3 * dm, transB=True, bias=bqkv)
+        else:
+            for i in range(3):
+                gemm(xs[i], wqkv, qkv, T, dm, dm, lda=dm, ldb=dm, ldc=3 * dm, transB=True,
+                     bias=bqkv[i * dm:(i + 1) * dm], b_off=i * dm * dm, c_off=i * dm)
+        # which blocks are normalised: galerkin -> (K, V), fourier -> (Q, K)
+        blocks = {"kv": (1, 2), "qk": (1, 0), None: ()}[norm_on]
+        rstd = []
+        for blk in blocks:
+            r = torch.empty((T, H), dtype=torch.float32, device=query.device)
+            _launch("headnorm_fwd", 8.0 * T * dm, 8.0 * T * dm, lib.gb200_headnorm_fwd, dev, ptr(qkv), 3 * dm,
+                    blk * dm, T, H, dk, eps, ptr(r), st)
+            rstd.append(r)
+        aff = {0: (None, None), 1: (None, None), 2: (None, None)}
+        if blocks:
+            aff[blocks[0]] = (g1, b1)
+            aff[blocks[1]] = (g2, b2)
+        ops = [_hop(qkv, 3 * dm, i * dm, False, *aff[i]) for i in range(3)]
+        A = torch.empty((B, H, d, d), dtype=torch.float32, device=query.device)
+        nsplit = lib.gb200_attn_suggest_nsplit(B, H, n)
+        ws_bytes = lib.gb200_attn_xty_workspace_bytes(B, H, d, nsplit)
+        ws = workspace(ws_bytes, qkv)
+        xty_work = (2.0 * B * H * n * d * d, 4.0 * (2 * T * dm + T * p))
+        xm_work = (2.0 * B * H * n * d * d, 4.0 * (T * dm + T * p + T * H * d))
+        _launch("attn_xty", *xty_work, lib.gb200_attn_xty, dev, ops[1], ops[2], ptr(pos), B, H, n, dk, p, scale,
+                ptr(keep_mask), ptr(A), nsplit, ptr(ws), ws_bytes, st)
+        out = torch.empty((B, n, H * d), dtype=torch.float32, device=query.device)
+        _launch("attn_xm", *xm_work, lib.gb200_attn_xm, dev, ops[0], ptr(pos), ptr(A), 0, B, H, n, dk, p,
+                ptr(out), H * d, 0, 1, 1.0, st)
+        ctx.save_for_backward(query, key, value, pos, wqkv, g1, b1, g2, b2, keep_mask, qkv, A, *rstd)
+        ctx.cfg = cfg
+        ctx.set_materialize_grads(False)
+        return out, A
+
+    @staticmethod
+    def backward(ctx, dout, dA_ext):
+        (query, key, value, pos, wqkv, g1, b1, g2, b2, keep_mask, qkv, A, *rstd) = ctx.saved_tensors
+        H, dk, p, eps, norm_on, scale, self_attn = ctx.cfg
+        lib = _lib.load()
+        B, n, dm = query.shape
+        T, d = B * n, dk + p
+        dev, st = _dev(query), stream_of(query)
+        dout = torch.zeros((B, n, H * d), dtype=torch.float32, device=query.device) if dout is None \
+            else dout.contiguous()
+        blocks = {"kv": (1, 2), "qk": (1, 0), None: ()}[norm_on]
+        aff = {0: (None, None), 1: (None, None), 2: (None, None)}
+        if blocks:
+            aff[blocks[0]] = (g1, b1)
+            aff[blocks[1]] = (g2, b2)
+        ops = [_hop(qkv, 3 * dm, i * dm, False, *aff[i]) for i in range(3)]
+        do_op = _hop(dout, H * d, 0, True)
+        # G = scale * mask2 * (Q~^T dO [+ external grad of A])
+        G = torch.empty((B, H, d, d), dtype=torch.float32, device=query.device)
+        xty_work = (2.0 * B * H * n * d * d, 4.0 * (T * dm + T * p + T * H * d))
+        xm_work = (2.0 * B * H * n * d * d, 4.0 * (2 * T * dm + T * p))
+        nsplit = lib.gb200_attn_suggest_nsplit(B, H, n)
+        ws_bytes = lib.gb200_attn_xty_workspace_bytes(B, H, d, nsplit)
+        ws = workspace(ws_bytes, qkv)
+        if dA_ext is None:       # the usual case: nobody differentiates through the returned A
+            _launch("attn_xty", *xty_work, lib.gb200_attn_xty, dev, ops[0], do_op, ptr(pos), B, H, n, dk, p,
+                    scale, ptr(keep_mask), ptr(G), nsplit, ptr(ws), ws_bytes, st)
+        else:
+            _launch("attn_xty", *xty_work, lib.gb200_attn_xty, dev, ops[0], do_op, ptr(pos), B, H, n, dk, p, 1.0,
+                    None, ptr(G), nsplit, ptr(ws), ws_bytes, st)
+            G = (G + dA_ext) * scale
+            if keep_mask is not None:
+                G = G * (2.0 * keep_mask.to(G.dtype))
+            G = G.contiguous()
+        dqkv = torch.empty((T, 3 * dm), dtype=torch.float32, device=query.device)
+        # dQ~ = dO A^T ; dV~ = K~ G ; dK~ = V~ G^T   (position columns carry no gradient)
+        _launch("attn_xm", *xm_work, lib.gb200_attn_xm, dev, do_op, ptr(pos), ptr(A), 1, B, H, n, dk, p, ptr(dqkv),
+                3 * dm, 0, 0, 1.0, st)
+        _launch("attn_xm", *xm_work, lib.gb200_attn_xm, dev, ops[1], ptr(pos), ptr(G), 0, B, H, n, dk, p, ptr(dqkv),
+                3 * dm, 2 * dm, 0, 1.0, st)
+        _launch("attn_xm", *xm_work, lib.gb200_attn_xm, dev, ops[2], ptr(pos), ptr(G), 1, B, H, n, dk, p, ptr(dqkv),
+                3 * dm, dm, 0, 1.0, st)
+        dgb = [None, None, None, None]
+        for j, blk in enumerate(blocks):
+            gamma = (g1, g2)[j]
+            dg = torch.empty_like(gamma)
+            db = torch.empty_like(gamma)
+            wsb = lib.gb200_headnorm_bwd_workspace_bytes(T, H, dk)
+            w2 = workspace(wsb, qkv)
+            _launch("headnorm_bwd", 14.0 * T * dm, 12.0 * T * dm, lib.gb200_headnorm_bwd, dev, ptr(dqkv), 3 * dm,
+                    blk * dm, ptr(qkv), 3 * dm, blk * dm, ptr(rstd[j]), ptr(gamma), T, H, dk, ptr(dg), ptr(db), 0,
+                    ptr(w2), wsb, st)
+            dgb[2 * j], dgb[2 * j + 1] = dg, db
+        # projection backward
+        dwqkv = torch.empty_like(wqkv)
+        dbqkv = torch.empty(3 * dm, dtype=torch.float32, device=query.device)
+        colsum(dqkv, T, 3 * dm, 3 * dm, dbqkv)
+        xs = [t.reshape(T, dm) for t in (query, key, value)]
+        dq = dk_ = dv = None
+        if self_attn:
+            gemm(dqkv, xs[0], dwqkv, 3 * dm, dm, T, lda=3 * dm, ldb=dm, ldc=dm, transA=True)
+            if ctx.needs_input_grad[0]:
+                dq = torch.empty_like(query)
+                gemm(dqkv, wqkv, dq, T, dm, 3 * dm, lda=3 * dm, ldb=dm, ldc=dm)
+        else:
+            grads = []
+            for i in range(3):
+                gemm(dqkv, xs[i], dwqkv, dm, dm, T, lda=3 * dm, ldb=dm, ldc=dm, transA=True, a_off=i * dm,
+                     c_off=i * dm * dm)
+                gi = None
+                if ctx.needs_input_grad[i]:
+                    gi = torch.empty_like(query)
+                    gemm(dqkv, wqkv, gi, T, dm, dm, lda=3 * dm, ldb=dm, ldc=dm, a_off=i * dm, b_off=i * dm * dm)
+                grads.append(gi)
+            dq, dk_, dv = grads
+        return (dq, dk_, dv, None, dwqkv, dbqkv, dgb[0], dgb[1], dgb[2], dgb[3], None, None)
+
+
+def linear_attention(query, key, value, pos, wqkv, bqkv, norm_params, keep_mask, *, n_head, pos_dim,
+                     eps, attention_type, self_attn):
+    """Returns (head-merged output (B, n, H*(d_k+p)), A (B,H,d,d))."""
+    B, n, dm = query.shape
+    dk = dm // n_head
+    p = pos_dim if pos is not None else 0
+    d = dk + p
+    if attention_type == "galerkin":
+        norm_on, scale = ("kv" if norm_params is not None else None), 1.0 / n
+    else:
+        norm_on, scale = ("qk" if norm_params is not None else None), 1.0 / (math.sqrt(d) * n)
+    g1 = b1 = g2 = b2 = None
+    if norm_params is not None:
+        g1, b1, g2, b2 = norm_params
+    cfg = (n_head, dk, p, float(eps), norm_on, float(scale), bool(self_attn))
+    pos_c = None if pos is None else pos.contiguous()
+    return _LinearAttentionFn.apply(query.contiguous(), key.contiguous(), value.contiguous(), pos_c, wqkv, bqkv,
+                                    g1, b1, g2, b2, keep_mask, cfg)
+
+
+# ------------------------------------------------------------------------------------------
+# Spectral convolution
+# ------------------------------------------------------------------------------------------
+_twiddle_cache = {}
+
+
+def _twiddles(n, m, device, two_d):
+    """(cos, sin)(2 pi k j / n) tables, computed in float64 once per (n, m, device)."""
+    key = (n, m, str(device), two_d)
+    tw = _twiddle_cache.get(key)
+    if tw is None:
+        j = torch.arange(n, dtype=torch.float64)
+        ky = torch.arange(m, dtype=torch.float64)
+        th = 2.0 * math.pi * torch.outer(ky, j) / n
+        twY = torch.stack([th.cos(), th.sin()], -1).to(torch.float32).to(device).contiguous()
+        twX = None
+        if two_d:
+            r = torch.arange(2 * m)
+            kx = torch.where(r < m, r, n - 2 * m + r).to(torch.float64)
+            ps = 2.0 * math.pi * torch.outer(kx, j) / n
+            twX = torch.stack([ps.cos(), ps.sin()], -1).to(torch.float32).to(device).contiguous()
+        tw = (twY, twX)
+        _twiddle_cache[key] = tw
+    return tw
+
+
+def _ydft(x, R, n, C, m, twY, scale, hermitian):
+    lib = _lib.load()
+    out = torch.empty((R, m, C, 2), dtype=torch.float32, device=x.device)
+    nsplit = lib.gb200_spectral_suggest_ysplit(R, C, n)
+    ws_bytes = lib.gb200_spectral_ydft_workspace_bytes(R, C, m, nsplit)
+    ws = workspace(ws_bytes, x)
+    _launch("spectral_ydft", 4.0 * R * n * C * m, 4.0 * R * n * C + 8.0 * R * m * C, lib.gb200_spectral_ydft,
+            _dev(x), ptr(x), R, n, C, m, ptr(twY), scale, int(hermitian), ptr(out), nsplit, ptr(ws), ws_bytes,
+            stream_of(x))
+    return out
+
+
+def _xdft(t, B, n, m, C, twX, scale, inverse):
+    lib = _lib.load()
+    shape = (B, n, m, C, 2) if inverse else (B, 2 * m, m, C, 2)
+    out = torch.empty(shape, dtype=torch.float32, device=t.device)
+    _launch("spectral_xdft", 16.0 * B * n * m * m * C, 8.0 * B * (n + 2 * m) * m * C, lib.gb200_spectral_xdft,
+            _dev(t), ptr(t), B, n, m, C, ptr(twX), scale, int(inverse), ptr(out), stream_of(t))
+    return out
+
+
+def _yidft_epi(Z, R, n, m, Co, twY, scale, hermitian, x2, Ci, Wm, bias, act, want_z):
+    lib = _lib.load()
+    y = torch.empty((R, n, Co), dtype=torch.float32, device=Z.device)
+    z = torch.empty_like(y) if want_z else None
+    _launch("spectral_yidft_epilogue", R * n * Co * (4.0 * m + 2.0 * Ci),
+            4.0 * R * n * (Ci + Co * (1 + want_z)) + 8.0 * R * m * Co + 4.0 * Ci * Co,
+            lib.gb200_spectral_yidft_epilogue, _dev(Z), ptr(Z), R, n, m, Co, ptr(twY), scale, int(hermitian),
+            ptr(x2), Ci, ptr(Wm), ptr(bias), act, ptr(y), ptr(z), stream_of(Z))
+    return y, z
+
+
+class _SpectralConvFn(torch.autograd.Function):
+    """act( irfft( W . rfft(x)[modes] ) + x @ Wl^T + bl ), channel-last, 1-D or 2-D
+    (libs/layers.py:1077-1106 and :1153-1197).  Optionally also returns the kept-mode block of
+    out_ft (B, halves*M2, Co, 2) for the `return_freq` contract."""
+
+    @staticmethod
+    def forward(ctx, x, xf, wl, bl, fw0, fw1, modes, act, two_d):
+        # x feeds the pointwise residual path, xf the transform (xf is x unless the module's
+        # input dropout is active: libs/layers.py:1083-1084, 1172-1173)
+        require_cuda_f32(x, xf, wl, bl, fw0, fw1)
+        same = xf is None
+        xf = x if same else xf
+        lib = _lib.load()
+        m = modes
+        if two_d:
+            B, n, n2, Ci = x.shape
+            assert n == n2
+        else:
+            B, n, Ci = x.shape
+        Co = wl.shape[0]
+        if 2 * m > n and two_d:
+            raise NotImplementedError(f"SpectralConv2d: 2*modes={2*m} > n={n} (overlapping mode blocks)")
+        if m > n // 2 + 1:
+            raise NotImplementedError(f"SpectralConv: modes={m} > n//2+1 for n={n}")
+        twY, twX = _twiddles(n, m, x.device, two_d)
+        dev, st = _dev(x), stream_of(x)
+        halves, M2 = (2, m * m) if two_d else (1, m)
+        if two_d:
+            T1 = _ydft(xf, B * n, n, Ci, m, twY, 1.0, False)
+            Xf = _xdft(T1, B, n, m, Ci, twX, 1.0 / n, False)
+        else:
+            Xf = _ydft(xf, B, n, Ci, m, twY, 1.0 / math.sqrt(n), False)
+        Of = torch.empty((B, halves * M2, Co, 2), dtype=torch.float32, device=x.device)
+        mix_work = (8.0 * B * halves * M2 * Ci * Co, 8.0 * halves * M2 * (Ci * Co + B * (Ci + Co)))
+        _launch("spectral_mix", *mix_work, lib.gb200_spectral_mix_fwd, dev, ptr(Xf), ptr(fw0), ptr(fw1), B, halves,
+                M2, Ci, Co, ptr(Of), st)
+        wm = wl.t().contiguous()                      # (Ci, Co): coalesced over output channels
+        need_z = act != 0 and (x.requires_grad or wl.requires_grad or fw0.requires_grad)
+        if two_d:
+            Z = _xdft(Of, B, n, m, Co, twX, 1.0, True)
+            y, z = _yidft_epi(Z, B * n, n, m, Co, twY, 1.0 / n, True, x, Ci, wm, bl, act, need_z)
+            y = y.view(B, n, n, Co)
+        else:
+            y, z = _yidft_epi(Of, B, n, m, Co, twY, 1.0 / math.sqrt(n), True, x, Ci, wm, bl, act, need_z)
+        ctx.save_for_backward(x, wl, fw0, fw1, Xf, z)
+        ctx.cfg = (m, act, two_d, bl is not None, same)
+        ctx.mark_non_differentiable(Of)
+        return y, Of
+
+    @staticmethod
+    def backward(ctx, gy, _gof):
+        x, wl, fw0, fw1, Xf, z = ctx.saved_tensors
+        m, act, two_d, has_bias, same = ctx.cfg
+        lib = _lib.load()
+        if two_d:
+            B, n, _, Ci = x.shape
+        else:
+            B, n, Ci = x.shape
+        Co = wl.shape[0]
+        P = B * n * n if two_d else B * n
+        twY, twX = _twiddles(n, m, x.device, two_d)
+        dev, st = _dev(x), stream_of(x)
+        halves, M2 = (2, m * m) if two_d else (1, m)
+        gy = gy.contiguous()
+        gz = epilogue_bwd(gy, P, Co, z=z, act=act) if act != 0 else gy
+        # adjoint of the inverse transform:  dO^ = (c_ky s) * DFT(gz) on the kept modes
+        if two_d:
+            dZ = _ydft(gz, B * n, n, Co, m, twY, 1.0 / n, True)
+            dO = _xdft(dZ, B, n, m, Co, twX, 1.0, False)
+        else:
+            dO = _ydft(gz, B, n, Co, m, twY, 1.0 / math.sqrt(n), True)
+        need_dx = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        dXf = torch.empty((B, halves * M2, Ci, 2), dtype=torch.float32, device=x.device) if need_dx else None
+        dfw0 = torch.empty_like(fw0) if ctx.needs_input_grad[4] else None
+        dfw1 = torch.empty_like(fw1) if (fw1 is not None and dfw0 is not None) else None
+        mix_work = (16.0 * B * halves * M2 * Ci * Co, 8.0 * halves * M2 * (2 * Ci * Co + 2 * B * (Ci + Co)))
+        _launch("spectral_mix", *mix_work, lib.gb200_spectral_mix_bwd, dev, ptr(Xf), ptr(dO), ptr(fw0), ptr(fw1), B,
+                halves, M2, Ci, Co, ptr(dXf), ptr(dfw0), ptr(dfw1), 0, st)
+        dx = dxf = dwl = dbl = None
+        if need_dx:
+            # adjoint of the forward transform + the pointwise path  gz @ Wl, one fused kernel
+            wres = wl if same else torch.zeros_like(wl)
+            if two_d:
+                dT1 = _xdft(dXf, B, n, m, Ci, twX, 1.0 / n, True)
+                dx, _ = _yidft_epi(dT1, B * n, n, m, Ci, twY, 1.0, False, gz, Co, wres, None, 0, False)
+            else:
+                dx, _ = _yidft_epi(dXf, B, n, m, Ci, twY, 1.0 / math.sqrt(n), False, gz, Co, wres, None, 0, False)
+            dx = dx.view(x.shape)
+            if not same:
+                dxf = dx
+                dx = torch.empty_like(x)
+                gemm(gz, wl, dx, P, Ci, Co, lda=Co, ldb=Ci, ldc=Ci)
+        if ctx.needs_input_grad[2]:
+            dwl = torch.empty_like(wl)
+            gemm(gz, x, dwl, Co, Ci, P, lda=Co, ldb=Ci, ldc=Ci, transA=True)
+        if has_bias and ctx.needs_input_grad[3]:
+            dbl = torch.empty(Co, dtype=torch.float32, device=x.device)
+            colsum(gz, P, Co, Co, dbl)
+        return dx, dxf, dwl, dbl, dfw0, dfw1, None, None, None
+
+
+def spectral_conv(x, wl, bl, fw0, fw1, *, modes, act, two_d, x_transform=None):
+    """x_transform: the (dropped-out) tensor fed to the transform when it differs from x."""
+    xf = None if x_transform is None else x_transform.contiguous()
+    return _SpectralConvFn.apply(x.contiguous(), xf, wl, bl, fw0, fw1, int(modes), ACT[act], bool(two_d))

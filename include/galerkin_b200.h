@@ -1,0 +1,156 @@
+/* libgalerkin_b200 -- C ABI of the B200-native (sm_100a) Galerkin/Fourier attention encoder and
+ * spectral-convolution decoder operators.
+ *
+ * The reference (scaomath/galerkin-transformer) has no FFI: its hot path is eager PyTorch.  Each
+ * entry point below therefore cites the reference Python lines it replaces; INTEGRATION.md
+ * shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 data unless the name says otherwise; the
+ *     caller (PyTorch) owns every buffer including outputs and workspaces; the library never
+ *     allocates device memory and never synchronises the host;
+ *   - `device` is the CUDA ordinal the buffers live on, `stream` a cudaStream_t passed as void*;
+ *     all work is enqueued on that stream and is CUDA-graph capturable;
+ *   - return value: 0 (GB200_OK) on success, non-zero otherwise with a human-readable message
+ *     from gb200_last_error() (thread-local); no exception ever crosses the boundary;
+ *   - matrices are row-major; `ld*` are row strides in floats;
+ *   - split reductions are two-stage with a fixed summation order: results are run-to-run
+ *     deterministic.
+ */
+#ifndef GALERKIN_B200_H_
+#define GALERKIN_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GB200_OK 0
+#define GB200_ERR_INVALID 1
+#define GB200_ERR_CUDA 2
+
+#define GB200_ACT_NONE 0
+#define GB200_ACT_RELU 1
+#define GB200_ACT_SILU 2
+
+int gb200_version(void);
+const char* gb200_last_error(void);
+/* Number of kernels this library has launched since load (all threads). */
+unsigned long long gb200_launch_count(void);
+
+/* ------------------------------------------------------------------ dense layers ------------
+ * C[b] = R[b] + rscale * dropout_p( act( alpha * op(A[b]) . op(B[b]) + bias ) )   (+= C if accumulate)
+ *   op(A): transA ? A stored [K,M] : A stored [M,K];  op(B): transB ? B stored [N,K] : B stored [K,N]
+ *   Zout (optional): receives the pre-activation (alpha*AB + bias), needed by SiLU backward
+ *   dropout: Philox4x32-10 keyed by (seed, element index); the same key in backward regenerates
+ *            the mask, no mask tensor exists
+ * Replaces nn.Linear forward/backward on the hot path: libs/layers.py:837-839 (Q,K,V), :896-897
+ * (fc), :980-986 (FeedForward), :1083 and :1172 (SpectralConv residual), libs/model.py:615-617,
+ * :629 (SpectralRegressor fc / regressor), and the residual adds of libs/model.py:124-132. */
+size_t gb200_gemm_workspace_bytes(int M, int N, int K, int nbatch, int ksplit);
+int gb200_gemm_suggest_ksplit(int M, int N, int K, int nbatch);
+int gb200_gemm(int device, const float* A, int lda, int transA, const float* B, int ldb, int transB,
+               float* C, int ldc, int M, int N, int K, int nbatch, long long strideA,
+               long long strideB, long long strideC, float alpha, const float* bias, int act,
+               float* Zout, int ldz, float drop_p, unsigned long long seed, const float* R, int ldr,
+               float rscale, int accumulate, int ksplit, float* workspace, size_t workspace_bytes,
+               void* stream);
+
+/* out[n] (+)= scale * sum_m X[m,n]            (bias gradients) */
+size_t gb200_colsum_workspace_bytes(long long M, int N);
+int gb200_colsum(int device, const float* X, int ld, long long M, int N, float scale, int accumulate,
+                 float* out, float* workspace, size_t workspace_bytes, void* stream);
+
+/* g = dy * rscale * dropmask(p, seed) * act'(.)   -- backward of the gb200_gemm epilogue.
+ * ReLU uses z if given, else the stored output y; SiLU needs z. */
+int gb200_epilogue_bwd(int device, const float* dy, int lddy, const float* z, int ldz, const float* y,
+                       int ldy, float* g, int ldg, long long M, int N, int act, float rscale,
+                       float drop_p, unsigned long long seed, void* stream);
+
+/* row LayerNorm over the last dimension (post-LN encoder variant, libs/model.py:128-129, 134-135) */
+int gb200_layernorm_fwd(int device, const float* x, long long rows, int width, const float* gamma,
+                        const float* beta, float eps, float* y, float* mean, float* rstd, void* stream);
+size_t gb200_layernorm_bwd_workspace_bytes(long long rows, int width);
+int gb200_layernorm_bwd(int device, const float* dy, const float* x, const float* mean, const float* rstd,
+                        const float* gamma, long long rows, int width, float* dx, float* dgamma,
+                        float* dbeta, int accumulate, float* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/* ------------------------------------------------------------------ attention core ----------
+ * Token-major "augmented head operand": row t, head h reads
+ *     [ pos[t,0..p) , gamma[h,:] * X[t, col0 + h*dk + :] + beta[h,:] ]      (augmented == 0)
+ *     X[t, col0 + h*(p+dk) + :]                                              (augmented == 1)
+ * which is what libs/layers.py:846-874 builds with per-head LayerNorm modules, torch.stack,
+ * pos.repeat and torch.cat -- here nothing of that is materialised. */
+typedef struct gb200_head_operand {
+    const float* ptr;
+    int ld;
+    int col0;
+    int augmented;
+    const float* gamma; /* (H, dk) or NULL */
+    const float* beta;  /* (H, dk) or NULL */
+} gb200_head_operand;
+
+/* per-head LayerNorm statistics: x[t, col0 + h*dk + :] <- (x - mean) * rstd in place; rstd (T,H).
+ * libs/layers.py:846-851, 859-864 (the affine part is applied on load by the kernels below) */
+int gb200_headnorm_fwd(int device, float* x, int ld, int col0, long long T, int H, int dk, float eps,
+                       float* rstd, void* stream);
+size_t gb200_headnorm_bwd_workspace_bytes(long long T, int H, int dk);
+/* dy (grad w.r.t. gamma*xhat+beta) is overwritten by the grad w.r.t. the un-normalised rows */
+int gb200_headnorm_bwd(int device, float* dy, int lddy, int dcol0, const float* xhat, int ldx, int xcol0,
+                       const float* rstd, const float* gamma, long long T, int H, int dk, float* dgamma,
+                       float* dbeta, int accumulate, float* workspace, size_t workspace_bytes,
+                       void* stream);
+
+/* out[b,h,i,j] = scale * (keep_mask ? 2*keep_mask : 1) * sum_t L~[b,t,h,i] * R~[b,t,h,j]
+ * forward: A = K~^T V~ / n with the reference's always-on p=0.5 dropout as an explicit keep-mask
+ * (libs/layers.py:723, 728, 730-731); backward: dA = Q~^T dO. */
+int gb200_attn_suggest_nsplit(int B, int H, int n);
+size_t gb200_attn_xty_workspace_bytes(int B, int H, int d, int nsplit);
+int gb200_attn_xty(int device, const gb200_head_operand* L, const gb200_head_operand* R, const float* pos,
+                   int B, int H, int n, int dk, int p, float scale, const unsigned char* keep_mask,
+                   float* out, int nsplit, float* workspace, size_t workspace_bytes, void* stream);
+
+/* out[b,t,h,:] = out_scale * L~[b,t,h,:] . (transM ? M[b,h]^T : M[b,h])
+ * out_augmented: written head-merged as (T, H*(p+dk)) -- libs/layers.py:733, 892-894;
+ * else the p position columns are dropped and (T, ldo) is written at ocol0 + h*dk (gradients). */
+int gb200_attn_xm(int device, const gb200_head_operand* L, const float* pos, const float* M, int transM,
+                  int B, int H, int n, int dk, int p, float* out, int ldo, int ocol0, int out_augmented,
+                  float out_scale, void* stream);
+
+/* ------------------------------------------------------------------ spectral convolution ----
+ * Mode-truncated DFT pipeline replacing rfft/rfft2 -> mode slice -> complex einsum -> zero pad ->
+ * irfft/irfft2 (libs/layers.py:1086-1101, 1175-1189).  Complex buffers are interleaved (re,im).
+ * twY: (m, n, 2) = (cos, sin)(2 pi ky Y / n);  twX: (2m, n, 2) for kx(r) = r (r<m) | n-2m+r. */
+int gb200_spectral_suggest_ysplit(long long R, int C, int n);
+size_t gb200_spectral_ydft_workspace_bytes(long long R, int C, int m, int nsplit);
+/* out[R,ky,c] = scale * (hermitian ? c_ky : 1) * sum_Y x[R,Y,c] e^{-i 2pi ky Y/n} */
+int gb200_spectral_ydft(int device, const float* x, long long R, int n, int C, int m, const float* twY,
+                        float scale, int hermitian, float* out, int nsplit, float* workspace,
+                        size_t workspace_bytes, void* stream);
+/* inverse == 0: out[b,r,ky,c] = scale * sum_X in[b,X,ky,c] e^{-i 2pi kx(r) X/n}
+ * inverse == 1: out[b,X,ky,c] = scale * sum_r in[b,r,ky,c] e^{+i 2pi kx(r) X/n} */
+int gb200_spectral_xdft(int device, const float* in, int B, int n, int m, int C, const float* twX,
+                        float scale, int inverse, float* out, void* stream);
+/* O[b,q,o] = sum_i X[b,q,i] * W_half(q)[i,o,q']   complex_matmul_{1d,2d}: libs/layers.py:1068-1075,
+ * 1144-1151.  halves = 1 (1-D, W0 only) or 2 (2-D, W0 = fourier_weight[0], W1 = fourier_weight[1]);
+ * M2 = modes per half (m or m*m). */
+int gb200_spectral_mix_fwd(int device, const float* Xf, const float* W0, const float* W1, int B, int halves,
+                           int M2, int Ci, int Co, float* Of, void* stream);
+/* dX = dO . conj(W) (skipped if NULL);  dW (+)= sum_b conj(X) . dO (skipped if dW0 NULL) */
+int gb200_spectral_mix_bwd(int device, const float* Xf, const float* dO, const float* W0, const float* W1,
+                           int B, int halves, int M2, int Ci, int Co, float* dX, float* dW0, float* dW1,
+                           int accumulate_dw, void* stream);
+/* y[R,Y,o] = act( scale * sum_ky c_ky Re(Z[R,ky,o] e^{+i 2pi ky Y/n}) + sum_i x2[R,Y,i] Wm[i,o] + bias[o] )
+ * i.e. irfft along the last axis fused with the residual nn.Linear, bias and SiLU
+ * (libs/layers.py:1083, 1098-1101 / 1172, 1187-1189).  zout (optional) receives the pre-activation. */
+int gb200_spectral_yidft_epilogue(int device, const float* Z, long long R, int n, int m, int Co,
+                                  const float* twY, float scale, int hermitian, const float* x2, int Ci,
+                                  const float* Wm, const float* bias, int act, float* y, float* zout,
+                                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GALERKIN_B200_H_ */

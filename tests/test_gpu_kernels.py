@@ -1,0 +1,227 @@
+"""GPU: each C-ABI kernel against a plain PyTorch fp64 evaluation of the same expression
+(tolerances are fp32 round-off: the SIMT path does exact-fp32 FMAs)."""
+import math
+
+import pytest
+import torch
+
+from galerkin_transformer_b200 import _lib, functional as GF
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 2e-6
+
+
+def rn(*s, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed + sum(s))
+    return torch.randn(*s, generator=g).to(DEV)
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (5, 7, 3), (64, 64, 16), (130, 70, 33), (257, 129, 130),
+                                   (1000, 384, 128), (3, 128, 1030)])
+@pytest.mark.parametrize("tA,tB", [(False, True), (False, False), (True, False), (True, True)])
+def test_gemm_layouts(M, N, K, tA, tB):
+    A = rn(K, M) if tA else rn(M, K)
+    B = rn(N, K, seed=1) if tB else rn(K, N, seed=1)
+    C = torch.empty(M, N, device=DEV)
+    GF.gemm(A, B, C, M, N, K, lda=A.shape[1], ldb=B.shape[1], ldc=N, transA=tA, transB=tB)
+    ref = (A.double().t() if tA else A.double()) @ (B.double().t() if tB else B.double())
+    assert rel_l2(C, ref) < TOL
+
+
+@pytest.mark.parametrize("ksplit", [1, 3, 16])
+def test_gemm_splitk_epilogue_is_deterministic(ksplit):
+    M, N, K = 96, 80, 4000
+    A, B, bias, R = rn(K, M), rn(K, N, seed=1), rn(N, seed=2), rn(M, N, seed=3)
+    outs = []
+    for _ in range(2):
+        C = torch.empty(M, N, device=DEV)
+        Z = torch.empty(M, N, device=DEV)
+        GF.gemm(A, B, C, M, N, K, lda=M, ldb=N, ldc=N, transA=True, alpha=0.5, bias=bias, act=2, zout=Z,
+                ldz=N, residual=R, ldr=N, rscale=-1.0, ksplit=ksplit)
+        outs.append(C)
+    z = 0.5 * A.double().t() @ B.double() + bias.double()
+    ref = R.double() - torch.nn.functional.silu(z)
+    assert rel_l2(outs[0], ref) < 5e-6 and rel_l2(Z, z) < 5e-6
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_gemm_accumulate_and_offsets():
+    M, N, K1, K2 = 50, 20, 12, 2
+    x1, x2, W, b = rn(M, K1), rn(M, K2, seed=1), rn(N, K1 + K2, seed=2), rn(N, seed=3)
+    y = GF.linear_cat(x1, x2, W, b)
+    ref = torch.cat([x1, x2], -1).double() @ W.double().t() + b.double()
+    assert rel_l2(y, ref) < TOL
+
+
+def test_fused_dropout_statistics_and_backward_consistency():
+    M, N, K, p = 512, 256, 64, 0.3
+    x = rn(M, K).requires_grad_(True)
+    W = rn(N, K, seed=1).requires_grad_(True)
+    torch.manual_seed(3)
+    y = GF.linear(x, W, None, act="relu", drop_p=p)
+    dense = torch.relu(x.detach().double() @ W.detach().double().t())
+    kept = (y != 0) & (dense > 0)
+    frac = kept.sum().item() / (dense > 0).sum().item()
+    assert abs(frac - (1 - p)) < 0.01                       # keep probability
+    assert rel_l2(y[kept], dense[kept] / (1 - p)) < TOL     # inverted-dropout scale
+    # backward regenerates the same mask: grad flows only through kept, positive entries
+    y.sum().backward()
+    mask = kept.double() / (1 - p)
+    assert rel_l2(x.grad, mask @ W.detach().double()) < 1e-5
+    assert rel_l2(W.grad, mask.t() @ x.detach().double()) < 1e-5
+
+
+@pytest.mark.parametrize("act", ["none", "relu", "silu"])
+def test_linear_autograd(act):
+    x = rn(3, 37, 24).requires_grad_(True)
+    W = rn(40, 24, seed=1).requires_grad_(True)
+    b = rn(40, seed=2).requires_grad_(True)
+    R = rn(3, 37, 40, seed=3).requires_grad_(True)
+    y = GF.linear(x, W, b, act=act, residual=R, rscale=-1.0)
+    cot = rn(3, 37, 40, seed=4)
+    grads = torch.autograd.grad((y * cot).sum(), [x, W, b, R])
+    xd, Wd, bd, Rd = [t.detach().double().requires_grad_(True) for t in (x, W, b, R)]
+    z = xd @ Wd.t() + bd
+    a = {"none": z, "relu": torch.relu(z), "silu": torch.nn.functional.silu(z)}[act]
+    yr = Rd - a
+    gr = torch.autograd.grad((yr * cot.double()).sum(), [xd, Wd, bd, Rd])
+    assert rel_l2(y, yr) < TOL
+    for g, r in zip(grads, gr):
+        assert rel_l2(g, r) < 1e-5
+
+
+def test_layernorm_fwd_bwd():
+    x = rn(1000, 48).requires_grad_(True)
+    g = (1 + 0.3 * rn(48, seed=1)).requires_grad_(True)
+    b = rn(48, seed=2).requires_grad_(True)
+    y = GF.layer_norm(x, g, b, 1e-5)
+    cot = rn(1000, 48, seed=3)
+    grads = torch.autograd.grad((y * cot).sum(), [x, g, b])
+    xd, gd, bd = [t.detach().double().requires_grad_(True) for t in (x, g, b)]
+    yr = torch.nn.functional.layer_norm(xd, (48,), gd, bd, 1e-5)
+    gr = torch.autograd.grad((yr * cot.double()).sum(), [xd, gd, bd])
+    assert rel_l2(y, yr) < TOL
+    for a, r in zip(grads, gr):
+        assert rel_l2(a, r) < 1e-5
+
+
+@pytest.mark.parametrize("B,H,n,dk,p", [(2, 4, 49, 8, 2), (1, 1, 300, 48, 2), (3, 2, 1000, 16, 1),
+                                        (2, 1, 130, 96, 1), (2, 4, 77, 32, 0)])
+def test_attention_core_kernels(B, H, n, dk, p):
+    lib = _lib.load()
+    dm, d, T = H * dk, dk + p, B * n
+    qkv = rn(T, 3 * dm)
+    pos = torch.rand(B, n, max(p, 1), device=DEV)[..., :p].contiguous() if p else None
+    gam, bet = 1 + 0.2 * rn(H, dk, seed=1), 0.2 * rn(H, dk, seed=2)
+    dev, st = 0, torch.cuda.current_stream().cuda_stream
+
+    def aug(block, g=None, b=None):
+        t = qkv[:, block * dm:(block + 1) * dm].double().view(B, n, H, dk)
+        if g is not None:
+            t = t * g.double() + b.double()
+        t = t.permute(0, 2, 1, 3)
+        if p:
+            t = torch.cat([pos.double().unsqueeze(1).expand(-1, H, -1, -1), t], -1)
+        return t                                             # (B,H,n,d)
+    k, v, q = aug(1, gam, bet), aug(2), aug(0)
+    mask = (torch.rand(B, H, d, d, device=DEV) > 0.5).to(torch.uint8)
+    A = torch.empty(B, H, d, d, device=DEV)
+    ops = [GF._hop(qkv, 3 * dm, i * dm, False, *((gam, bet) if i == 1 else (None, None))) for i in range(3)]
+    nsplit = lib.gb200_attn_suggest_nsplit(B, H, n)
+    wsb = lib.gb200_attn_xty_workspace_bytes(B, H, d, nsplit)
+    ws = _lib.workspace(wsb, qkv)
+    _lib.check(lib.gb200_attn_xty(dev, ops[1], ops[2], _lib.ptr(pos), B, H, n, dk, p, 1.0 / n, _lib.ptr(mask),
+                                  _lib.ptr(A), nsplit, _lib.ptr(ws), wsb, st))
+    Aref = (k.transpose(-1, -2) @ v) / n * (2.0 * mask.double())
+    assert rel_l2(A, Aref) < 5e-6
+    out = torch.empty(B, n, H * d, device=DEV)
+    _lib.check(lib.gb200_attn_xm(dev, ops[0], _lib.ptr(pos), _lib.ptr(A), 0, B, H, n, dk, p, _lib.ptr(out), H * d,
+                                 0, 1, 1.0, st))
+    oref = (q @ A.double()).permute(0, 2, 1, 3).reshape(B, n, H * d)
+    assert rel_l2(out, oref) < 5e-6
+    # transposed multiply, non-augmented output (gradient layout)
+    dq = torch.zeros(T, 3 * dm, device=DEV)
+    do = GF._hop(out, H * d, 0, True)
+    _lib.check(lib.gb200_attn_xm(dev, do, _lib.ptr(pos), _lib.ptr(A), 1, B, H, n, dk, p, _lib.ptr(dq), 3 * dm, dm,
+                                 0, 1.0, st))
+    ref = (oref.view(B, n, H, d).permute(0, 2, 1, 3) @ A.double().transpose(-1, -2))[..., p:]
+    ref = ref.permute(0, 2, 1, 3).reshape(T, dm)
+    assert rel_l2(dq[:, dm:2 * dm], ref) < 5e-6
+    assert dq[:, :dm].abs().max() == 0 and dq[:, 2 * dm:].abs().max() == 0
+
+
+def test_headnorm_fwd_bwd():
+    lib = _lib.load()
+    T, H, dk, eps = 777, 4, 32, 1e-7
+    dm = H * dk
+    raw = rn(T, 3 * dm)
+    gam = 1 + 0.2 * rn(H, dk, seed=1)
+    buf = raw.clone()
+    rstd = torch.empty(T, H, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.gb200_headnorm_fwd(0, _lib.ptr(buf), 3 * dm, dm, T, H, dk, eps, _lib.ptr(rstd), st))
+    x = raw[:, dm:2 * dm].double().view(T, H, dk).requires_grad_(True)
+    mu, var = x.mean(-1, keepdim=True), x.var(-1, unbiased=False, keepdim=True)
+    xhat = (x - mu) / torch.sqrt(var + eps)
+    assert rel_l2(buf[:, dm:2 * dm], xhat.reshape(T, dm)) < TOL
+    assert torch.equal(buf[:, :dm], raw[:, :dm]) and torch.equal(buf[:, 2 * dm:], raw[:, 2 * dm:])
+    dy = rn(T, 3 * dm, seed=5)
+    y = xhat * gam.double()
+    gx, = torch.autograd.grad((y * dy[:, dm:2 * dm].double().view(T, H, dk)).sum(), x)
+    dbuf = dy.clone()
+    dg, db = torch.empty(H, dk, device=DEV), torch.empty(H, dk, device=DEV)
+    wsb = lib.gb200_headnorm_bwd_workspace_bytes(T, H, dk)
+    ws = _lib.workspace(wsb, buf)
+    _lib.check(lib.gb200_headnorm_bwd(0, _lib.ptr(dbuf), 3 * dm, dm, _lib.ptr(buf), 3 * dm, dm, _lib.ptr(rstd),
+                                      _lib.ptr(gam), T, H, dk, _lib.ptr(dg), _lib.ptr(db), 0, _lib.ptr(ws), wsb, st))
+    assert rel_l2(dbuf[:, dm:2 * dm], gx.reshape(T, dm)) < 1e-5
+    dyk = dy[:, dm:2 * dm].double().view(T, H, dk)
+    assert rel_l2(dg, (dyk * xhat.detach()).sum(0)) < 1e-5 and rel_l2(db, dyk.sum(0)) < 1e-5
+
+
+def _sc_ref(x, wl, bl, fw0, fw1, m, act, two_d):
+    """torch.fft evaluation of the spectral layer in fp64 (independent of the kernels' DFT form)."""
+    xd = x.double()
+    res = xd @ wl.double().t() + bl.double()
+    if two_d:
+        B, n = x.shape[0], x.shape[1]
+        xf = torch.fft.rfft2(xd.permute(0, 3, 1, 2), s=(n, n), norm="ortho")
+        of = xf.new_zeros(B, wl.shape[0], n, n // 2 + 1)
+        of[:, :, :m, :m] = torch.einsum("bixy,ioxy->boxy", xf[:, :, :m, :m], torch.view_as_complex(fw0.double()))
+        of[:, :, -m:, :m] = torch.einsum("bixy,ioxy->boxy", xf[:, :, -m:, :m], torch.view_as_complex(fw1.double()))
+        y = torch.fft.irfft2(of, s=(n, n), norm="ortho").permute(0, 2, 3, 1)
+    else:
+        B, n = x.shape[0], x.shape[1]
+        xf = torch.fft.rfft(xd.permute(0, 2, 1), n=n, norm="ortho")
+        of = xf.new_zeros(B, wl.shape[0], n // 2 + 1)
+        of[:, :, :m] = torch.einsum("bix,iox->box", xf[:, :, :m], torch.view_as_complex(fw0.double()))
+        y = torch.fft.irfft(of, n=n, norm="ortho").permute(0, 2, 1)
+    z = y + res
+    return {"silu": torch.nn.functional.silu, "relu": torch.relu, "none": lambda t: t}[act](z)
+
+
+@pytest.mark.parametrize("shape,Co,m,act", [((2, 15, 15, 6), 5, 4, "silu"), ((1, 32, 32, 20), 20, 12, "silu"),
+                                            ((2, 141, 141, 8), 8, 12, "relu"), ((3, 16, 16, 4), 7, 8, "none"),
+                                            ((2, 64, 8), 6, 5, "silu"), ((2, 8192, 16), 12, 16, "silu"),
+                                            ((3, 45, 4), 4, 7, "relu"), ((1, 40, 3), 3, 20, "none")])
+def test_spectral_conv_forward_backward(shape, Co, m, act):
+    two_d = len(shape) == 4
+    Ci = shape[-1]
+    x = rn(*shape).requires_grad_(True)
+    wl = (0.3 * rn(Co, Ci, seed=1)).requires_grad_(True)
+    bl = (0.3 * rn(Co, seed=2)).requires_grad_(True)
+    wshape = (Ci, Co, m, m, 2) if two_d else (Ci, Co, m, 2)
+    fw0 = (0.3 * rn(*wshape, seed=3)).requires_grad_(True)
+    fw1 = (0.3 * rn(*wshape, seed=4)).requires_grad_(True) if two_d else None
+    y, _ = GF.spectral_conv(x, wl, bl, fw0, fw1, modes=m, act=act, two_d=two_d)
+    params = [x, wl, bl, fw0] + ([fw1] if two_d else [])
+    cot = rn(*y.shape, seed=9)
+    grads = torch.autograd.grad((y * cot).sum(), params)
+    pd = [t.detach().clone().requires_grad_(True) for t in params]
+    yr = _sc_ref(pd[0], pd[1], pd[2], pd[3], pd[4] if two_d else None, m, act, two_d)
+    gr = torch.autograd.grad((yr * cot.double()).sum(), pd)
+    assert rel_l2(y, yr) < 5e-6
+    for g, r in zip(grads, gr):
+        assert rel_l2(g, r) < 2e-5
