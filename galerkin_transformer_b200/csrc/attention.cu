@@ -131,15 +131,9 @@ __global__ void headnorm_bwd_kernel(float* __restrict__ dy, int lddy, int dcol0,
 __global__ void headnorm_bwd_reduce_kernel(const float* __restrict__ part, int nblocks, int W,
                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
                                            int accumulate) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= W) return;
-    float sg = 0.f, sb = 0.f;
-    for (int b = 0; b < nblocks; ++b) {
-        sg += part[((long long)b * 2 + 0) * W + c];
-        sb += part[((long long)b * 2 + 1) * W + c];
-    }
-    dgamma[c] = accumulate ? dgamma[c] + sg : sg;
-    dbeta[c] = accumulate ? dbeta[c] + sb : sb;
+    // blockIdx.y = 0: dgamma, 1: dbeta
+    reduce_partials_2d(part + (long long)blockIdx.y * W, nblocks, 2LL * W, W, 1.f, accumulate,
+                       blockIdx.y == 0 ? dgamma : dbeta);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -333,8 +327,8 @@ extern "C" int gb200_headnorm_bwd(int device, float* dy, int lddy, int dcol0, co
     cudaStream_t st = as_stream(stream);
     headnorm_bwd_kernel<<<nblocks, 256, smem, st>>>(dy, lddy, dcol0, xhat, ldx, xcol0, rstd, gamma, T, H, dk,
                                                    workspace);
-    headnorm_bwd_reduce_kernel<<<cdiv(H * dk, 128), 128, 0, st>>>(workspace, nblocks, H * dk, dgamma, dbeta,
-                                                                 accumulate);
+    headnorm_bwd_reduce_kernel<<<dim3(cdiv(H * dk, 32), 2), dim3(32, 8), 0, st>>>(workspace, nblocks, H * dk, dgamma,
+                                                                                dbeta, accumulate);
     return check_launch("gb200_headnorm_bwd", 2);
 }
 

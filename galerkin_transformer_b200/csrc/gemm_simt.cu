@@ -179,12 +179,7 @@ __global__ void colsum_partial_kernel(const float* __restrict__ X, int M, int N,
 }
 __global__ void colsum_final_kernel(const float* __restrict__ part, int nparts, int N, float scale,
                                     int accumulate, float* __restrict__ out) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    float s = 0.f;
-    for (int p = 0; p < nparts; ++p) s += part[(long long)p * N + n];
-    s *= scale;
-    out[n] = accumulate ? out[n] + s : s;
+    reduce_partials_2d(part, nparts, N, N, scale, accumulate, out);
 }
 
 // g = dy * rscale * dropmask * act'(z)   (backward of the GEMM epilogue, elementwise)
@@ -291,7 +286,7 @@ extern "C" int gb200_colsum(int device, const float* X, int ld, long long M, int
     cudaStream_t st = as_stream(stream);
     colsum_partial_kernel<<<dim3(cdiv(N, 32), nparts), dim3(32, 8), 0, st>>>(X, (int)M, N, ld, rows_per_block,
                                                                                workspace);
-    colsum_final_kernel<<<cdiv(N, 128), 128, 0, st>>>(workspace, nparts, N, scale, accumulate, out);
+    colsum_final_kernel<<<cdiv(N, 32), dim3(32, 8), 0, st>>>(workspace, nparts, N, scale, accumulate, out);
     return check_launch("gb200_colsum", 2);
 }
 

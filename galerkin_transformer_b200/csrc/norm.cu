@@ -69,15 +69,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(
 __global__ void layernorm_bwd_reduce_kernel(const float* __restrict__ part, int nblocks, int width,
                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
                                             int accumulate) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= width) return;
-    float sg = 0.f, sb = 0.f;
-    for (int b = 0; b < nblocks; ++b) {
-        sg += part[((long long)b * 2 + 0) * width + c];
-        sb += part[((long long)b * 2 + 1) * width + c];
-    }
-    dgamma[c] = accumulate ? dgamma[c] + sg : sg;
-    dbeta[c] = accumulate ? dbeta[c] + sb : sb;
+    reduce_partials_2d(part + (long long)blockIdx.y * width, nblocks, 2LL * width, width, 1.f, accumulate,
+                       blockIdx.y == 0 ? dgamma : dbeta);
 }
 
 static int ln_blocks(long long rows) {
@@ -120,7 +113,7 @@ extern "C" int gb200_layernorm_bwd(int device, const float* dy, const float* x, 
         cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaStream_t st = as_stream(stream);
     layernorm_bwd_kernel<<<nblocks, LN_WARPS * 32, smem, st>>>(dy, x, mean, rstd, gamma, rows, width, dx, workspace);
-    layernorm_bwd_reduce_kernel<<<cdiv(width, 128), 128, 0, st>>>(workspace, nblocks, width, dgamma, dbeta,
-                                                                 accumulate);
+    layernorm_bwd_reduce_kernel<<<dim3(cdiv(width, 32), 2), dim3(32, 8), 0, st>>>(workspace, nblocks, width, dgamma,
+                                                                                dbeta, accumulate);
     return check_launch("gb200_layernorm_bwd", 2);
 }

@@ -117,11 +117,14 @@ class _LinearFn(torch.autograd.Function):
         M, K = x.shape
         N = weight.shape[0]
         y = torch.empty((M, N), dtype=torch.float32, device=x.device)
-        need_z = act == ACT["silu"] and (x.requires_grad or weight.requires_grad)
+        # backward needs act'(z): SiLU always from z; ReLU from the stored output unless a residual
+        # was folded into it
+        need_z = (act == ACT["silu"] or (act == ACT["relu"] and residual is not None)) \
+            and (x.requires_grad or weight.requires_grad)
         z = torch.empty_like(y) if need_z else None
         gemm(x, weight, y, M, N, K, lda=K, ldb=K, ldc=N, transB=True, bias=bias, act=act, zout=z, ldz=N,
              drop_p=drop_p, seed=seed, residual=residual, ldr=N, rscale=rscale)
-        ctx.save_for_backward(x, weight, z, y if act == ACT["relu"] else None)
+        ctx.save_for_backward(x, weight, z, y if (act == ACT["relu"] and z is None) else None)
         ctx.cfg = (act, rscale, drop_p, seed, bias is not None, residual is not None)
         return y
 

@@ -318,10 +318,22 @@ class UpScaler(nn.Module):
 class _ConfiguredModel(nn.Module):
     """kwargs -> attributes, missing keys read as None (libs/model.py:25-30, 832-835)."""
 
+    KNOWN_KEYS = ['node_feats', 'edge_feats', 'pos_dim', 'n_targets', 'n_hidden', 'num_feat_layers',
+                  'num_encoder_layers', 'n_head', 'pred_len', 'n_freq_targets', 'dim_feedforward',
+                  'feat_extract_type', 'graph_activation', 'attention_type', 'xavier_init', 'diagonal_weight',
+                  'symmetric_init', 'layer_norm', 'attn_norm', 'batch_norm', 'spacial_residual',
+                  'return_attn_weight', 'seq_len', 'bulk_regression', 'decoder_type', 'freq_dim',
+                  'num_regressor_layers', 'fourier_modes', 'dropout', 'downscaler_dropout',
+                  'upscaler_dropout', 'upsample_mode', 'downsample_mode', 'last_activation', 'debug']
+
     def _absorb(self, kwargs):
         self.config = defaultdict(lambda: None, **kwargs)
-        for key in list(self.config.keys()) + ADDITIONAL_ATTR:
+        for key in list(self.config.keys()) + ADDITIONAL_ATTR + self.KNOWN_KEYS:
             setattr(self, key, self.config[key])
+        self.symmetric_init = bool(self.symmetric_init)
+        self.batch_norm = bool(self.batch_norm)
+        self.layer_norm = bool(self.layer_norm)
+        self.last_activation = True if self.last_activation is None else self.last_activation
         self.dim_feedforward = _default(self.dim_feedforward, 2 * self.n_hidden)
         self.dropout = _default(self.dropout, 0.05)
         self.dpo = nn.Dropout(self.dropout)

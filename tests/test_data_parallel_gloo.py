@@ -57,14 +57,20 @@ def test_flat_bucket_allreduce_matches_full_batch():
     assert torch.allclose(got[0], full, rtol=1e-5, atol=1e-7)
 
 
-def test_bucket_views_alias_parameter_grads():
+def test_bucket_pack_points_grads_at_flat_views():
     model = _model()
     bucket = FlatGradBucket(model)
     x, y = _data()
+    bucket.zero()
+    assert all(p.grad is None for p in model.parameters())
     ((model(x) - y) ** 2).mean().backward()
+    ref = [p.grad.clone() for p in model.parameters()]
+    bucket.all_reduce()                       # single process: no-op, grads untouched
+    assert all(torch.equal(p.grad, r) for p, r in zip(model.parameters(), ref))
+    bucket.pack()
     off = 0
-    for p in model.parameters():
+    for p, r in zip(model.parameters(), ref):
         assert p.grad.data_ptr() == bucket.flat.data_ptr() + 4 * off
+        assert torch.equal(p.grad, r)
         off += p.numel()
-    assert bucket.nbytes == 4 * off and bucket.flat.abs().sum() > 0
-    assert bucket.all_reduce() is None        # single process: no-op
+    assert bucket.nbytes == 4 * off

