@@ -10,6 +10,7 @@ from .layers import FeedForward, Identity, SimpleAttention, SpectralConv1d, Spec
 from .model import (DownScaler, FourierTransformer2D, FourierTransformer2DLite,  # noqa: F401
                     PointwiseRegressor, SimpleTransformer, SimpleTransformerEncoderLayer,
                     SpectralRegressor, UpScaler)
+from .functional import get_precision, set_precision  # noqa: F401
 from .utils import scaler_sizes, set_attn_dropout  # noqa: F401
 
 __version__ = "0.1.0"

@@ -33,11 +33,17 @@ SIGNATURES = {
     "gb200_version": (c_int, []),
     "gb200_last_error": (ctypes.c_char_p, []),
     "gb200_launch_count": (c_ull, []),
+    "gb200_set_rng_offset_ptr": (c_int, [c_vp]),
     "gb200_gemm_workspace_bytes": (c_sz, [c_int] * 5),
     "gb200_gemm_suggest_ksplit": (c_int, [c_int] * 4),
     "gb200_gemm": (c_int, [c_int, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_int,
                            c_int, c_ll, c_ll, c_ll, c_float, c_vp, c_int, c_vp, c_int, c_float, c_ull,
                            c_vp, c_int, c_float, c_int, c_int, c_vp, c_sz, c_vp]),
+    "gb200_gemm_tc_supported": (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int]),
+    "gb200_gemm_tc_suggest_ksplit": (c_int, [c_int] * 3),
+    "gb200_gemm_tc": (c_int, [c_int, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_int,
+                              c_float, c_vp, c_int, c_vp, c_int, c_float, c_ull, c_vp, c_int, c_float, c_int,
+                              c_int, c_vp, c_sz, c_vp]),
     "gb200_colsum_workspace_bytes": (c_sz, [c_ll, c_int]),
     "gb200_colsum": (c_int, [c_int, c_vp, c_int, c_ll, c_int, c_float, c_int, c_vp, c_vp, c_sz, c_vp]),
     "gb200_epilogue_bwd": (c_int, [c_int, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_ll, c_int,

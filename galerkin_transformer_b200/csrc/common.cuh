@@ -13,6 +13,7 @@ namespace gb200 {
 void set_error(const char* fmt, ...);
 int check_launch(const char* what, int nkernels = 1);  // cudaGetLastError -> error string; counts launches
 void use_device(int device);                 // thread-local cached cudaSetDevice
+const unsigned long long* rng_offset_ptr();  // device counter added to every dropout seed (graph-safe RNG)
 
 #define GB_REQUIRE(cond, ...)                                  \
     do {                                                       \

@@ -1,0 +1,34 @@
+// Epilogue shared by the SIMT and tcgen05 GEMMs:
+//   v = alpha*acc + bias[n];  Z = v;  v = act(v);  v *= dropout(seed, element);  C = R + rscale*v  (+= C)
+#pragma once
+#include "common.cuh"
+
+namespace gb200 {
+
+struct GemmEpilogue {
+    float* C; int ldc; long long sC;
+    float alpha;
+    const float* bias;
+    int act;
+    float* Z; int ldz;
+    float drop_p; unsigned long long seed;
+    const unsigned long long* seed_off;   // device-side step counter (or null): seed += *seed_off
+    const float* R; int ldr; float rscale;
+    int accumulate;
+
+    __device__ __forceinline__ void store(int batch, int m, int n, int M, int N, float acc) const {
+        float v = alpha * acc;
+        if (bias) v += bias[n];
+        if (Z) Z[(long long)batch * sC + (long long)m * ldz + n] = v;
+        v = act_apply(act, v);
+        if (drop_p > 0.f)
+            v *= dropout_scale(drop_p, seed + (seed_off ? *seed_off : 0ull), ((unsigned long long)batch * M + m) * N + n);
+        float* c = C + (long long)batch * sC + (long long)m * ldc + n;
+        if (R) v = R[(long long)batch * sC + (long long)m * ldr + n] + rscale * v;
+        else v *= rscale;
+        if (accumulate) v += *c;
+        *c = v;
+    }
+};
+
+}  // namespace gb200

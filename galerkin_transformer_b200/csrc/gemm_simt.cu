@@ -12,40 +12,21 @@
 // libs/layers.py:837-839 (Q,K,V projections), :896-897 (fc), :980-986 (FeedForward),
 // :1083/:1172 (SpectralConv residual Linear) and libs/model.py:615-617, 629 (regressor).
 #include "common.cuh"
+#include "gemm_epilogue.cuh"
 
 namespace gb200 {
 
 constexpr int BM = 64, BN = 64, BK = 16, PAD = 4, NT = 256;
 
 struct GemmArgs {
-    const float* A; const float* B; float* C;
-    int M, N, K, lda, ldb, ldc;
-    long long sA, sB, sC;
+    const float* A; const float* B;
+    int M, N, K, lda, ldb;
+    long long sA, sB;
     int nbatch, ksplit, kchunk;
-    float alpha;
-    const float* bias;
-    int act;
-    float* Z; int ldz;
-    float drop_p; unsigned long long seed;
-    const float* R; int ldr; float rscale;
-    int accumulate;
+    GemmEpilogue ep;
     float* ws;
     int vecA, vecB;
 };
-
-__device__ __forceinline__ void epilogue_store(const GemmArgs& g, int batch, int m, int n, float acc) {
-    float v = g.alpha * acc;
-    if (g.bias) v += g.bias[n];
-    if (g.Z) g.Z[(long long)batch * g.sC + (long long)m * g.ldz + n] = v;
-    v = act_apply(g.act, v);
-    if (g.drop_p > 0.f)
-        v *= dropout_scale(g.drop_p, g.seed, ((unsigned long long)batch * g.M + m) * g.N + n);
-    float* c = g.C + (long long)batch * g.sC + (long long)m * g.ldc + n;
-    if (g.R) v = g.R[(long long)batch * g.sC + (long long)m * g.ldr + n] + g.rscale * v;
-    else v *= g.rscale;
-    if (g.accumulate) v += *c;
-    *c = v;
-}
 
 // 4 consecutive elements along the contiguous storage dimension, zero-filled out of range.
 __device__ __forceinline__ float4 load4(const float* base, long long row, int ld, int col, int nrows,
@@ -139,7 +120,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmArgs g) {
             if (g.ksplit > 1)
                 g.ws[(((long long)batch * g.ksplit + split) * g.M + m) * g.N + n] = acc[i][j];
             else
-                epilogue_store(g, batch, m, n, acc[i][j]);
+                g.ep.store(batch, m, n, g.M, g.N, acc[i][j]);
         }
     }
 }
@@ -155,7 +136,7 @@ __global__ void splitk_reduce_kernel(GemmArgs g) {
         float s = 0.f;
         const float* p = g.ws + ((long long)batch * g.ksplit * g.M + m) * g.N + n;
         for (int k = 0; k < g.ksplit; ++k) s += p[(long long)k * g.M * g.N];
-        epilogue_store(g, batch, m, n, s);
+        g.ep.store(batch, m, n, g.M, g.N, s);
     }
 }
 
@@ -186,8 +167,9 @@ __global__ void colsum_final_kernel(const float* __restrict__ part, int nparts, 
 __global__ void epilogue_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ z,
                                     int ldz, const float* __restrict__ y, int ldy, float* __restrict__ gout,
                                     int ldg, long long M, int N, int act, float rscale, float drop_p,
-                                    unsigned long long seed) {
+                                    unsigned long long seed, const unsigned long long* seed_off) {
     const long long total = M * N;
+    if (drop_p > 0.f && seed_off) seed += *seed_off;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x) {
         const long long m = e / N;
@@ -240,12 +222,13 @@ extern "C" int gb200_gemm(int device, const float* A, int lda, int transA, const
     if (ksplit < 1) ksplit = 1;
     if (K == 0) ksplit = 1;
     GemmArgs g;
-    g.A = A; g.B = B; g.C = C; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
-    g.sA = strideA; g.sB = strideB; g.sC = strideC; g.nbatch = nbatch; g.ksplit = ksplit;
+    g.A = A; g.B = B; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb;
+    g.sA = strideA; g.sB = strideB; g.nbatch = nbatch; g.ksplit = ksplit;
+    g.ep.C = C; g.ep.ldc = ldc; g.ep.sC = strideC;
     int ktiles = cdiv(K > 0 ? K : 1, BK);
     g.kchunk = cdiv(ktiles, ksplit) * BK;
-    g.alpha = alpha; g.bias = bias; g.act = act; g.Z = Zout; g.ldz = ldz; g.drop_p = drop_p;
-    g.seed = seed; g.R = R; g.ldr = ldr; g.rscale = rscale; g.accumulate = accumulate;
+    g.ep.alpha = alpha; g.ep.bias = bias; g.ep.act = act; g.ep.Z = Zout; g.ep.ldz = ldz; g.ep.drop_p = drop_p;
+    g.ep.seed = seed; g.ep.seed_off = rng_offset_ptr(); g.ep.R = R; g.ep.ldr = ldr; g.ep.rscale = rscale; g.ep.accumulate = accumulate;
     g.ws = workspace;
     g.vecA = ((uintptr_t)A % 16 == 0) && (lda % 4 == 0) && (strideA % 4 == 0);
     g.vecB = ((uintptr_t)B % 16 == 0) && (ldb % 4 == 0) && (strideB % 4 == 0);
@@ -302,6 +285,6 @@ extern "C" int gb200_epilogue_bwd(int device, const float* dy, int lddy, const f
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     epilogue_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(dy, lddy, z, ldz, y, ldy, g, ldg, M, N, act,
-                                                               rscale, drop_p, seed);
+                                                               rscale, drop_p, seed, rng_offset_ptr());
     return check_launch("gb200_epilogue_bwd");
 }

@@ -1,0 +1,541 @@
+// tcgen05 (5th-gen tensor core) TF32 GEMM for sm_100a with the library's fused epilogue.
+//
+//   C = R + rscale * drop( act( alpha * op(A) . op(B) + bias ) )           fp32 in, fp32 out
+//
+//   * operands are fp32 in HBM and are consumed as TF32 by `tcgen05.mma.kind::tf32`
+//     (10-bit mantissa; ~4e-4 relative error per contraction);
+//   * tiles are staged global -> shared by TMA (`cp.async.bulk.tensor.2d`, SWIZZLE_128B,
+//     out-of-range rows/columns zero-filled so ragged M/N/K need no special casing);
+//   * accumulators live in TMEM (128 lanes x BN fp32 columns), read back with `tcgen05.ld`;
+//   * both operand majors are supported through the UMMA descriptors, so the three GEMMs of a
+//     Linear layer (y = x W^T, dx = g W, dW = g^T x) all run here without any transpose copy:
+//         A K-major : stored [M, K]      A MN-major : stored [K, M]
+//         B K-major : stored [N, K]      B MN-major : stored [K, N]
+//   * warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane),
+//     warps 2-5 = TF32 round-to-nearest converters during the main loop, then the epilogue (each owns
+//     one 32-lane TMEM quarter); 3-stage mbarrier ring (full -> converted -> empty); two CTAs fit per
+//     SM so one tile's epilogue overlaps another tile's main loop;
+//   * split-K (weight gradients reduce over all tokens) writes fp32 partials that
+//     `splitk_reduce_kernel` sums in fixed order (deterministic).
+//
+// All waits are bounded: a descriptor/protocol bug traps instead of hanging the device.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "gemm_epilogue.cuh"
+
+namespace gb200 {
+
+constexpr int TC_BM = 128, TC_BK = 32, TC_STAGES = 3, TC_THREADS = 192;
+constexpr uint32_t TC_SPIN_LIMIT = 1u << 26;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    const uint32_t addr = smem_u32(bar);
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (++spins > TC_SPIN_LIMIT) {
+            printf("gb200 gemm_tc: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y,
+                   blockIdx.z, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// UMMA shared-memory descriptor, SWIZZLE_128B (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+// [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout (2 = SW128)
+// MN-major 32-bit operands must use layout 1 = SWIZZLE_128B_BASE32B (128-byte rows, 32-byte swizzle
+// granules, 4-row atoms; cutlass sm100_common.inl: "for mn-major tf32 operands, SW128_32B is the only
+// available smem layout"), filled by TMA's CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+template <int LAYOUT>
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)LAYOUT << 61;
+    return d;
+}
+
+struct TcArgs {
+    GemmEpilogue ep;      // shared with the SIMT kernel: bias/act/dropout/residual/Z/C
+    int M, N, K;
+    int ksplit, kchunk;   // kchunk is a multiple of TC_BK
+    float* ws;
+    int vec4;             // C/R/Z/ws rows are 16-byte aligned and N % 4 == 0: float4 epilogue
+};
+
+// activation with fast intrinsics (the TF32 path is not bit-exact fp32 anyway)
+template <int ACT>
+__device__ __forceinline__ float act_fast(float v) {
+    if (ACT == ACT_RELU) return fmaxf(v, 0.f);
+    if (ACT == ACT_SILU) return __fdividef(v, 1.f + __expf(-v));
+    return v;
+}
+
+// Coalesced float4 epilogue for one warp's 32 accumulator rows staged in shared memory.
+// Compile-time activation / dropout; residual, Z and accumulate are warp-uniform runtime switches.
+template <int ACT, bool DROP>
+__device__ __forceinline__ void tc_epilogue_vec4(const TcArgs& g, const float* __restrict__ stage, int DS, int lane,
+                                                 int rbase, int n0, int ncols, unsigned long long seed) {
+    const GemmEpilogue& ep = g.ep;
+    constexpr int RB = 8;                        // rows in flight per thread
+    const bool hasR = ep.R != nullptr, hasZ = ep.Z != nullptr, accum = ep.accumulate != 0;
+    const float alpha = ep.alpha, rscale = ep.rscale, p = ep.drop_p;
+    const int nrows = min(32, g.M - rbase);
+    for (int c = lane * 4; c < ncols; c += 128) {
+        const int n = n0 + c;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ep.bias) bv = *reinterpret_cast<const float4*>(ep.bias + n);
+        const float* rp = hasR ? ep.R + (long long)rbase * ep.ldr + n : nullptr;
+        float* cp = ep.C + (long long)rbase * ep.ldc + n;
+        float* zp = hasZ ? ep.Z + (long long)rbase * ep.ldz + n : nullptr;
+#pragma unroll 1
+        for (int r0 = 0; r0 < nrows; r0 += RB) {
+            float4 acc[RB], rv[RB];
+#pragma unroll
+            for (int i = 0; i < RB; ++i) {
+                acc[i] = *reinterpret_cast<const float4*>(&stage[(r0 + i) * DS + c]);
+                rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r0 + i < nrows) {
+                    if (hasR) rv[i] = *reinterpret_cast<const float4*>(rp + (long long)(r0 + i) * ep.ldr);
+                    if (accum) {
+                        const float4 cv = *reinterpret_cast<const float4*>(cp + (long long)(r0 + i) * ep.ldc);
+                        rv[i].x += cv.x; rv[i].y += cv.y; rv[i].z += cv.z; rv[i].w += cv.w;
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < RB; ++i) {
+                if (r0 + i >= nrows) break;
+                float4 z = make_float4(fmaf(alpha, acc[i].x, bv.x), fmaf(alpha, acc[i].y, bv.y),
+                                       fmaf(alpha, acc[i].z, bv.z), fmaf(alpha, acc[i].w, bv.w));
+                if (hasZ) *reinterpret_cast<float4*>(zp + (long long)(r0 + i) * ep.ldz) = z;
+                float4 v = make_float4(act_fast<ACT>(z.x), act_fast<ACT>(z.y), act_fast<ACT>(z.z), act_fast<ACT>(z.w));
+                if (DROP) {
+                    const unsigned long long e = (unsigned long long)(rbase + r0 + i) * g.N + n;
+                    v.x *= dropout_scale(p, seed, e);     v.y *= dropout_scale(p, seed, e + 1);
+                    v.z *= dropout_scale(p, seed, e + 2); v.w *= dropout_scale(p, seed, e + 3);
+                }
+                *reinterpret_cast<float4*>(cp + (long long)(r0 + i) * ep.ldc) =
+                    make_float4(fmaf(rscale, v.x, rv[i].x), fmaf(rscale, v.y, rv[i].y), fmaf(rscale, v.z, rv[i].z),
+                                fmaf(rscale, v.w, rv[i].w));
+            }
+        }
+    }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                             const __grid_constant__ CUtensorMap mapB, TcArgs g) {
+    constexpr int A_BYTES = TC_BM * TC_BK * 4;          // 16 KB
+    constexpr int B_BYTES = BN * TC_BK * 4;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte alignment is required by SWIZZLE_128B atoms
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + TC_STAGES;
+    uint64_t* conv_bar = empty_bar + TC_STAGES;
+    uint64_t* tmem_full = conv_bar + TC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+    const int split = blockIdx.z;
+    const int kbeg = split * g.kchunk;
+    const int kend = min(g.K, kbeg + g.kchunk);
+    const int nkb = (kend - kbeg + TC_BK - 1) / TC_BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+            mbar_init(&conv_bar[s], 4);          // one arrival per converter warp
+        }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    }
+    if (warp == 2) {   // TMEM allocation: BN fp32 columns x 128 lanes (power of two >= 32)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(BN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {   // ---------------- TMA producer ----------------
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % TC_STAGES;
+                const uint32_t ph = (kb / TC_STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* sa = smem + s * STAGE_BYTES;
+                uint8_t* sb = sa + A_BYTES;
+                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                const int k0 = kbeg + kb * TC_BK;
+                if (!A_MN) {
+                    tma_load_2d(sa, &mapA, &full_bar[s], k0, m0);                    // box {32 k, 128 m}
+                } else {
+#pragma unroll
+                    for (int j = 0; j < TC_BM / 32; ++j)                                // box {32 m, 32 k}
+                        tma_load_2d(sa + j * 4096, &mapA, &full_bar[s], m0 + 32 * j, k0);
+                }
+                if (!B_MN) {
+                    tma_load_2d(sb, &mapB, &full_bar[s], k0, n0);                    // box {32 k, BN n}
+                } else {
+#pragma unroll
+                    for (int j = 0; j < BN / 32; ++j)
+                        tma_load_2d(sb + j * 4096, &mapB, &full_bar[s], n0 + 32 * j, k0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {   // ---------------- MMA issuer ----------------
+            // instruction descriptor (cute UMMA::InstrDescriptor): D=F32, A=B=TF32, majors, N>>3, M>>4
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                                   ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                                   ((uint32_t)(TC_BM >> 4) << 24);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % TC_STAGES;
+                const uint32_t ph = (kb / TC_STAGES) & 1;
+                mbar_wait(&conv_bar[s], ph);     // tile landed (TMA) and rounded to TF32 (converter warps)
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+                for (int k = 0; k < TC_BK / 8; ++k) {
+                    // K-major (SW128): 8 tf32 = 32 bytes further along the 128-byte swizzled row; 8-row groups
+                    //   are 1024 B apart (SBO).
+                    // MN-major (SW128 base-32B): rows are k, 128 B each; 4-row swizzle atoms 512 B apart (SBO);
+                    //   8 k-rows per MMA = 1024 B; 32-wide MN blocks are 4096 B apart (LBO).
+                    const uint64_t ad = A_MN ? umma_desc<1>(sa + k * 1024, 4096, 512) : umma_desc<2>(sa + k * 32, 16, 1024);
+                    const uint64_t bd = B_MN ? umma_desc<1>(sb + k * 1024, 4096, 512) : umma_desc<2>(sb + k * 32, 16, 1024);
+                    tc_mma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0);
+                }
+                tc_commit(&empty_bar[s]);        // frees the stage once these MMAs have read it
+            }
+            tc_commit(tmem_full);                // accumulator complete
+        }
+    } else {               // ---------------- epilogue warps 2..5 ----------------
+        // TMEM -> registers (thread = accumulator row) -> shared memory (the pipeline stages are idle once
+        // tmem_full has fired) -> coalesced global epilogue (lane = output column).  Each warp only touches
+        // its own 32 rows, so no cross-warp synchronisation is needed.
+        // Main-loop duty: round every landed fp32 tile to TF32 with round-to-nearest (cvt.rna), in place.
+        // tcgen05.mma kind::tf32 would otherwise just drop the 13 low mantissa bits (truncation: a
+        // systematic -1e-3 relative bias per product); rounding makes the error zero-mean like cuBLAS TF32.
+        {
+            const int ct = threadIdx.x - 64;     // 0..127
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % TC_STAGES;
+                const uint32_t ph = (kb / TC_STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                float4* tile = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
+#pragma unroll 4
+                for (int i = ct; i < STAGE_BYTES / 16; i += 128) {
+                    float4 v = tile[i];
+                    uint32_t x, y, z, w;
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(x) : "f"(v.x));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(y) : "f"(v.y));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(z) : "f"(v.z));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(w) : "f"(v.w));
+                    tile[i] = make_float4(__uint_as_float(x), __uint_as_float(y), __uint_as_float(z),
+                                          __uint_as_float(w));
+                }
+                // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0)
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&conv_bar[s])) : "memory");
+            }
+        }
+        const int q = warp % 4;                  // TMEM lane quarter this warp may access
+        constexpr int DS = BN + 4;               // row pitch = 1 (mod 8) float4s: conflict-free float4 stores (thread = row)
+                                                 // and float4 loads (lane = 4 columns)
+        float* stage = reinterpret_cast<float*>(smem) + q * 32 * DS;
+        if (nkb > 0) {
+            mbar_wait(tmem_full, 0);
+            tc_fence_after();
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            if (nkb > 0) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                      "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+                      "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+                      "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(&stage[lane * DS + c0 + j]) =
+                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                __uint_as_float(v[j + 3]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        const int ncols = min(BN, g.N - n0);
+        const GemmEpilogue& ep = g.ep;
+        const unsigned long long seed = ep.seed + ((ep.drop_p > 0.f && ep.seed_off) ? *ep.seed_off : 0ull);
+        constexpr int RB = 8;                    // rows in flight per thread: 8 independent global loads
+        const int rbase = m0 + q * 32;
+        if (g.ksplit > 1 && g.vec4) {
+            // split-K: raw fp32 partials, coalesced float4 rows
+            const int nrows = min(32, g.M - rbase);
+            for (int c = lane * 4; c < ncols; c += 128)
+                for (int r = 0; r < nrows; ++r)
+                    *reinterpret_cast<float4*>(g.ws + ((long long)split * g.M + rbase + r) * g.N + n0 + c) =
+                        *reinterpret_cast<const float4*>(&stage[r * DS + c]);
+        } else if (g.vec4) {
+            const bool drop = ep.drop_p > 0.f;
+            if (ep.act == ACT_NONE) {
+                if (drop) tc_epilogue_vec4<ACT_NONE, true>(g, stage, DS, lane, rbase, n0, ncols, seed);
+                else tc_epilogue_vec4<ACT_NONE, false>(g, stage, DS, lane, rbase, n0, ncols, seed);
+            } else if (ep.act == ACT_RELU) {
+                if (drop) tc_epilogue_vec4<ACT_RELU, true>(g, stage, DS, lane, rbase, n0, ncols, seed);
+                else tc_epilogue_vec4<ACT_RELU, false>(g, stage, DS, lane, rbase, n0, ncols, seed);
+            } else {
+                if (drop) tc_epilogue_vec4<ACT_SILU, true>(g, stage, DS, lane, rbase, n0, ncols, seed);
+                else tc_epilogue_vec4<ACT_SILU, false>(g, stage, DS, lane, rbase, n0, ncols, seed);
+            }
+        } else {
+            for (int c = lane; c < ncols; c += 32) {
+                const int n = n0 + c;
+                const float bv = (g.ksplit == 1 && ep.bias) ? ep.bias[n] : 0.f;
+#pragma unroll 1
+                for (int r0 = 0; r0 < 32; r0 += RB) {
+                    float acc[RB], rv[RB], cv[RB];
+#pragma unroll
+                    for (int i = 0; i < RB; ++i) {
+                        const int row = rbase + r0 + i;
+                        acc[i] = stage[(r0 + i) * DS + c];
+                        const bool ok = row < g.M && g.ksplit == 1;
+                        rv[i] = (ok && ep.R) ? ep.R[(long long)row * ep.ldr + n] : 0.f;
+                        cv[i] = (ok && ep.accumulate) ? ep.C[(long long)row * ep.ldc + n] : 0.f;
+                    }
+#pragma unroll
+                    for (int i = 0; i < RB; ++i) {
+                        const int row = rbase + r0 + i;
+                        if (row >= g.M) continue;
+                        if (g.ksplit > 1) {
+                            g.ws[((long long)split * g.M + row) * g.N + n] = acc[i];
+                            continue;
+                        }
+                        float v = ep.alpha * acc[i] + bv;
+                        if (ep.Z) ep.Z[(long long)row * ep.ldz + n] = v;
+                        v = act_apply(ep.act, v);
+                        if (ep.drop_p > 0.f)
+                            v *= dropout_scale(ep.drop_p, seed, (unsigned long long)row * g.N + n);
+                        v = ep.R ? rv[i] + ep.rscale * v : ep.rscale * v;
+                        ep.C[(long long)row * ep.ldc + n] = v + cv[i];
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+    }
+}
+
+__global__ void tc_splitk_reduce_kernel(TcArgs g) {
+    const long long total = (long long)g.M * g.N;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(e % g.N);
+        const int m = (int)(e / g.N);
+        float s = 0.f;
+        for (int k = 0; k < g.ksplit; ++k) s += g.ws[(long long)k * total + e];
+        g.ep.store(0, m, n, g.M, g.N, s);
+    }
+}
+
+// ---- host side: tensor maps through the driver entry point (no link-time libcuda dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor map: `inner` contiguous elements per row, `outer` rows, row pitch ld floats.
+static bool make_map(CUtensorMap* m, const float* base, long long inner, long long outer, long long ld, int box_inner,
+                     int box_outer, CUtensorMapSwizzle swizzle) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& g, cudaStream_t st) {
+    constexpr int smem = TC_STAGES * (TC_BM * TC_BK * 4 + BN * TC_BK * 4) + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = true;
+    }
+    dim3 grid(cdiv(g.N, BN), cdiv(g.M, TC_BM), g.ksplit);
+    gemm_tc_kernel<BN, A_MN, B_MN><<<grid, TC_THREADS, smem, st>>>(ma, mb, g);
+    return 0;
+}
+
+}  // namespace gb200
+
+using namespace gb200;
+
+extern "C" int gb200_gemm_tc_supported(const float* A, int lda, const float* B, int ldb, int M, int N, int K) {
+    if (M < 1 || N < 8 || K < 8) return 0;
+    if (((uintptr_t)A % 16) || ((uintptr_t)B % 16) || (lda % 4) || (ldb % 4)) return 0;
+    return encode_fn() != nullptr;
+}
+
+// widest N tile that still gives every SM a CTA (two co-reside per SM); narrow outputs get narrow tiles
+static int pick_bn(int M, int N) {
+    const long long mt = cdiv(M, TC_BM);
+    if (N >= 128 && mt * cdiv(N, 128) >= 148) return 128;
+    if (N >= 64 && mt * cdiv(N, 64) >= 148) return 64;
+    if (N >= 128) return mt * cdiv(N, 32) >= 148 ? 32 : 128;   // tiny problems: fewer, fatter CTAs
+    return N >= 64 ? 64 : 32;
+}
+
+extern "C" int gb200_gemm_tc_suggest_ksplit(int M, int N, int K) {
+    const int bn = pick_bn(M, N);
+    long long tiles = (long long)cdiv(M, TC_BM) * cdiv(N, bn);
+    if (tiles >= 120 || K < 1024) return 1;
+    int want = (int)((2 * 148 + tiles - 1) / tiles);
+    int maxs = K / 256;
+    int s = want < maxs ? want : maxs;
+    return s < 1 ? 1 : (s > 64 ? 64 : s);
+}
+
+extern "C" int gb200_gemm_tc(int device, const float* A, int lda, int transA, const float* B, int ldb, int transB,
+                             float* C, int ldc, int M, int N, int K, float alpha, const float* bias, int act,
+                             float* Zout, int ldz, float drop_p, unsigned long long seed, const float* R, int ldr,
+                             float rscale, int accumulate, int ksplit, float* workspace, size_t workspace_bytes,
+                             void* stream) {
+    use_device(device);
+    GB_REQUIRE(A && B && C, "gb200_gemm_tc: null operand");
+    GB_REQUIRE(gb200_gemm_tc_supported(A, lda, B, ldb, M, N, K),
+               "gb200_gemm_tc: unsupported shape/alignment (M=%d N=%d K=%d lda=%d ldb=%d); use gb200_gemm", M, N, K,
+               lda, ldb);
+    GB_REQUIRE(act == ACT_NONE || act == ACT_RELU || act == ACT_SILU, "gb200_gemm_tc: unknown activation %d", act);
+    GB_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "gb200_gemm_tc: dropout p=%f outside [0,1)", drop_p);
+    if (ksplit < 1) ksplit = 1;
+    const bool a_mn = transA != 0;      // A stored [K, M]
+    const bool b_mn = transB == 0;      // B stored [K, N]
+    const int bn = pick_bn(M, N);
+    TcArgs g;
+    g.ep.C = C; g.ep.ldc = ldc; g.ep.sC = 0; g.ep.alpha = alpha; g.ep.bias = bias; g.ep.act = act; g.ep.Z = Zout;
+    g.ep.ldz = ldz; g.ep.drop_p = drop_p; g.ep.seed = seed; g.ep.seed_off = rng_offset_ptr(); g.ep.R = R; g.ep.ldr = ldr; g.ep.rscale = rscale;
+    g.ep.accumulate = accumulate;
+    g.M = M; g.N = N; g.K = K; g.ksplit = ksplit;
+    g.kchunk = cdiv(cdiv(K, TC_BK), ksplit) * TC_BK;
+    g.ksplit = cdiv(K, g.kchunk);
+    g.ws = workspace;
+    auto al16 = [](const void* p) { return ((uintptr_t)p % 16) == 0; };
+    g.vec4 = (N % 4 == 0) && al16(C) && (ldc % 4 == 0) && (!R || (al16(R) && ldr % 4 == 0)) &&
+             (!Zout || (al16(Zout) && ldz % 4 == 0)) && (!bias || al16(bias)) && (!workspace || al16(workspace));
+    if (g.ksplit > 1)
+        GB_REQUIRE(workspace && workspace_bytes >= (size_t)g.ksplit * M * N * sizeof(float),
+                   "gb200_gemm_tc: split-K workspace too small");
+    CUtensorMap ma, mb;
+    const CUtensorMapSwizzle SWK = CU_TENSOR_MAP_SWIZZLE_128B, SWMN = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    bool ok = a_mn ? make_map(&ma, A, M, K, lda, 32, 32, SWMN) : make_map(&ma, A, K, M, lda, 32, TC_BM, SWK);
+    ok = ok && (b_mn ? make_map(&mb, B, N, K, ldb, 32, 32, SWMN) : make_map(&mb, B, K, N, ldb, 32, bn, SWK));
+    GB_REQUIRE(ok, "gb200_gemm_tc: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d lda=%d ldb=%d)", M, N, K, lda, ldb);
+    cudaStream_t st = as_stream(stream);
+#define TC_DISPATCH(BNV)                                                               \
+    do {                                                                               \
+        if (!a_mn && !b_mn) launch_tc<BNV, false, false>(ma, mb, g, st);               \
+        else if (!a_mn && b_mn) launch_tc<BNV, false, true>(ma, mb, g, st);            \
+        else if (a_mn && !b_mn) launch_tc<BNV, true, false>(ma, mb, g, st);            \
+        else launch_tc<BNV, true, true>(ma, mb, g, st);                                \
+    } while (0)
+    if (bn == 128) TC_DISPATCH(128);
+    else if (bn == 64) TC_DISPATCH(64);
+    else TC_DISPATCH(32);
+#undef TC_DISPATCH
+    if (g.ksplit > 1) {
+        long long total = (long long)M * N;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        tc_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(g);
+    }
+    return check_launch("gb200_gemm_tc", g.ksplit > 1 ? 2 : 1);
+}

@@ -9,6 +9,9 @@ namespace gb200 {
 static thread_local char g_err[512] = "";
 static thread_local int g_device = -1;
 static std::atomic<unsigned long long> g_launches{0};
+static const unsigned long long* g_rng_offset = nullptr;
+
+const unsigned long long* rng_offset_ptr() { return g_rng_offset; }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -36,6 +39,10 @@ int check_launch(const char* what, int nkernels) {
 
 }  // namespace gb200
 
-extern "C" int gb200_version(void) { return 100; }
+extern "C" int gb200_version(void) { return 101; }
+extern "C" int gb200_set_rng_offset_ptr(const unsigned long long* device_counter) {
+    gb200::g_rng_offset = device_counter;
+    return GB200_OK;
+}
 extern "C" const char* gb200_last_error(void) { return gb200::g_err; }
 extern "C" unsigned long long gb200_launch_count(void) { return gb200::g_launches.load(); }

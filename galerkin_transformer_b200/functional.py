@@ -15,6 +15,21 @@ from ._lib import HeadOperand, check, ptr, stream_of, workspace, require_cuda_f3
 
 ACT = {"none": 0, None: 0, "identity": 0, "relu": 1, "silu": 2}
 
+# GEMM arithmetic: "tf32" = tcgen05 tensor cores (fp32 storage, TF32 multiplies, fp32 accumulate);
+# "fp32" = exact-fp32 SIMT FMAs everywhere (the precise mode used by the tight parity tests).
+_PRECISION = "tf32"
+
+
+def set_precision(mode):
+    """'tf32' (default, tensor cores) or 'fp32' (exact SIMT path)."""
+    global _PRECISION
+    assert mode in ("tf32", "fp32")
+    _PRECISION = mode
+
+
+def get_precision():
+    return _PRECISION
+
 _seed_lock = threading.Lock()
 _seed_counter = 0
 
@@ -31,6 +46,24 @@ def next_seed():
 
 def _dev(t):
     return t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+
+_rng_step = None
+
+
+def rng_step_counter(device=None):
+    """Device-side int64 step counter added to every fused-dropout seed (one per process/GPU).
+    `advance_rng()` bumps it with a tiny kernel, which -- unlike a Python-side seed -- still works when
+    the whole step is replayed from a CUDA graph (see graphs.py)."""
+    global _rng_step
+    if _rng_step is None:
+        _rng_step = torch.zeros(1, dtype=torch.int64, device=device or torch.device("cuda", torch.cuda.current_device()))
+        check(_lib.load().gb200_set_rng_offset_ptr(_rng_step.data_ptr()), "gb200_set_rng_offset_ptr")
+    return _rng_step
+
+
+def advance_rng():
+    rng_step_counter().add_(0x9E3779B1)
 
 
 class Profiler:
@@ -77,16 +110,25 @@ def gemm(A, B, C, M, N, K, *, lda, ldb, ldc, transA=False, transB=False, alpha=1
          ksplit=None, a_off=0, b_off=0, c_off=0):
     """C = R + rscale*drop(act(alpha*op(A).op(B)+bias)); offsets are in floats."""
     lib = _lib.load()
+    pa, pb = ptr(A) + 4 * a_off, ptr(B) + 4 * b_off
+    nbytes = 4.0 * (M * K + K * N + M * N * (1 + (residual is not None) + (zout is not None)))
+    lay = ("t" if transA else "n") + ("t" if transB else "n")
+    if _PRECISION == "tf32" and lib.gb200_gemm_tc_supported(pa, lda, pb, ldb, M, N, K):
+        if ksplit is None:
+            ksplit = lib.gb200_gemm_tc_suggest_ksplit(M, N, K)
+        ws_bytes = ksplit * M * N * 4 if ksplit > 1 else 0
+        ws = workspace(ws_bytes, C)
+        _launch("gemm_tc_" + lay, 2.0 * M * N * K, nbytes, lib.gb200_gemm_tc, _dev(C), pa, lda, int(transA), pb,
+                ldb, int(transB), ptr(C) + 4 * c_off, ldc, M, N, K, alpha, ptr(bias), act, ptr(zout), ldz, drop_p,
+                seed, ptr(residual), ldr, rscale, int(accumulate), ksplit, ptr(ws), ws_bytes, stream_of(C))
+        return
     if ksplit is None:
         ksplit = lib.gb200_gemm_suggest_ksplit(M, N, K, 1)
     ws_bytes = lib.gb200_gemm_workspace_bytes(M, N, K, 1, ksplit)
     ws = workspace(ws_bytes, C)
-    fam = "gemm_" + ("t" if transA else "n") + ("t" if transB else "n")
-    nbytes = 4.0 * (M * K + K * N + M * N * (1 + (residual is not None) + (zout is not None)))
-    _launch(fam, 2.0 * M * N * K, nbytes, lib.gb200_gemm, _dev(C), ptr(A) + 4 * a_off, lda, int(transA),
-            ptr(B) + 4 * b_off, ldb, int(transB), ptr(C) + 4 * c_off, ldc, M, N, K, 1, 0, 0, 0, alpha, ptr(bias),
-            act, ptr(zout), ldz, drop_p, seed, ptr(residual), ldr, rscale, int(accumulate), ksplit, ptr(ws),
-            ws_bytes, stream_of(C))
+    _launch("gemm_simt_" + lay, 2.0 * M * N * K, nbytes, lib.gb200_gemm, _dev(C), pa, lda, int(transA), pb, ldb,
+            int(transB), ptr(C) + 4 * c_off, ldc, M, N, K, 1, 0, 0, 0, alpha, ptr(bias), act, ptr(zout), ldz,
+            drop_p, seed, ptr(residual), ldr, rscale, int(accumulate), ksplit, ptr(ws), ws_bytes, stream_of(C))
 
 
 def colsum(X, M, N, ld, out, *, x_off=0, scale=1.0, accumulate=False):

@@ -40,17 +40,20 @@ class FlatGradBucket:
     def world_size(self):
         return dist.get_world_size(self.group) if dist.is_initialized() else 1
 
-    def pack(self):
-        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
+    def pack(self, grads=None):
+        """Copy gradients (default: each `p.grad`) into the bucket and re-point `p.grad` at its slices.
+        Pass `grads` explicitly when they live in static CUDA-graph buffers."""
+        if grads is None:
+            grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
         torch._foreach_copy_(self.views, grads)
         for p, v in zip(self.params, self.views):
             p.grad = v
 
-    def all_reduce(self):
+    def all_reduce(self, grads=None):
         """Average gradients over ranks (one collective); a no-op for a single process."""
         if not dist.is_initialized() or self.world_size() == 1:
             return
-        self.pack()
+        self.pack(grads)
         if dist.get_backend(self.group) == "nccl":
             dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
         else:

@@ -38,6 +38,10 @@ int gb200_version(void);
 const char* gb200_last_error(void);
 /* Number of kernels this library has launched since load (all threads). */
 unsigned long long gb200_launch_count(void);
+/* Graph-safe dropout: every fused-dropout kernel adds *device_counter (read on the device at run time) to
+ * its Philox seed.  Bumping the counter with a kernel inside a captured CUDA graph gives every replay fresh
+ * masks while forward and backward of one step still agree.  NULL (default) disables the offset. */
+int gb200_set_rng_offset_ptr(const unsigned long long* device_counter);
 
 /* ------------------------------------------------------------------ dense layers ------------
  * C[b] = R[b] + rscale * dropout_p( act( alpha * op(A[b]) . op(B[b]) + bias ) )   (+= C if accumulate)
@@ -56,6 +60,19 @@ int gb200_gemm(int device, const float* A, int lda, int transA, const float* B, 
                float* Zout, int ldz, float drop_p, unsigned long long seed, const float* R, int ldr,
                float rscale, int accumulate, int ksplit, float* workspace, size_t workspace_bytes,
                void* stream);
+
+/* Same contract as gb200_gemm (single batch), executed on the 5th-generation tensor cores:
+ * TMA-staged SWIZZLE_128B tiles, tcgen05.mma kind::tf32 (fp32 operands read as TF32, fp32 accumulate in
+ * TMEM), all four operand layouts without transpose copies, deterministic split-K.  Requires 16-byte
+ * aligned operands with lda, ldb multiples of 4 and N, K >= 8 (gb200_gemm_tc_supported); otherwise call
+ * gb200_gemm.  Relative error ~4e-4 per contraction (TF32), see DESIGN.md. */
+int gb200_gemm_tc_supported(const float* A, int lda, const float* B, int ldb, int M, int N, int K);
+int gb200_gemm_tc_suggest_ksplit(int M, int N, int K);
+int gb200_gemm_tc(int device, const float* A, int lda, int transA, const float* B, int ldb, int transB,
+                  float* C, int ldc, int M, int N, int K, float alpha, const float* bias, int act,
+                  float* Zout, int ldz, float drop_p, unsigned long long seed, const float* R, int ldr,
+                  float rscale, int accumulate, int ksplit, float* workspace, size_t workspace_bytes,
+                  void* stream);
 
 /* out[n] (+)= scale * sum_m X[m,n]            (bias gradients) */
 size_t gb200_colsum_workspace_bytes(long long M, int N);

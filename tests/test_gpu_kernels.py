@@ -11,6 +11,15 @@ from helpers import rel_l2
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 TOL = 2e-6
+TF32_TOL = 2e-3     # tcgen05 kind::tf32: 10-bit mantissa operands, fp32 accumulate
+
+
+@pytest.fixture(autouse=True)
+def _exact_fp32_by_default():
+    """Kernel tests check the exact-fp32 path unless they opt into the tensor-core path."""
+    GF.set_precision("fp32")
+    yield
+    GF.set_precision("tf32")
 
 
 def rn(*s, seed=0):
@@ -28,6 +37,66 @@ def test_gemm_layouts(M, N, K, tA, tB):
     GF.gemm(A, B, C, M, N, K, lda=A.shape[1], ldb=B.shape[1], ldc=N, transA=tA, transB=tB)
     ref = (A.double().t() if tA else A.double()) @ (B.double().t() if tB else B.double())
     assert rel_l2(C, ref) < TOL
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 32, 64), (200, 64, 40), (1000, 384, 128), (14792, 128, 136),
+                                   (300, 136, 128), (97, 24, 200), (4096, 256, 128)])
+@pytest.mark.parametrize("tA,tB", [(False, True), (False, False), (True, False), (True, True)])
+def test_gemm_tc_layouts(M, N, K, tA, tB):
+    """tcgen05 TF32 GEMM, all four operand majors, ragged M/N/K (TMA zero fill)."""
+    GF.set_precision("tf32")
+    Ms, Ks, Ns = -(-M // 4) * 4, -(-K // 4) * 4, -(-N // 4) * 4      # storage pitches: multiples of 4 floats
+    A = rn(K, Ms)[:, :M] if tA else rn(M, Ks)[:, :K]
+    B = rn(N, Ks, seed=1)[:, :K] if tB else rn(K, Ns, seed=1)[:, :N]
+    C = torch.zeros(M, N, device=DEV)
+    lib = _lib.load()
+    assert lib.gb200_gemm_tc_supported(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), M, N, K)
+    GF.Profiler.reset(); GF.Profiler.enabled = True
+    GF.gemm(A, B, C, M, N, K, lda=A.stride(0), ldb=B.stride(0), ldc=N, transA=tA, transB=tB)
+    GF.Profiler.enabled = False
+    assert GF.Profiler.records[-1][0].startswith("gemm_tc_"), "tensor-core path was not taken"
+    ref = (A.double().t() if tA else A.double()) @ (B.double().t() if tB else B.double())
+    assert rel_l2(C, ref) < TF32_TOL, rel_l2(C, ref)
+
+
+@pytest.mark.parametrize("ksplit", [1, 4, 29])
+def test_gemm_tc_splitk_epilogue(ksplit):
+    GF.set_precision("tf32")
+    M, N, K = 384, 128, 14792                         # the d(W_qkv) shape of the C3 encoder
+    A, B, bias, R = rn(K, M), rn(K, N, seed=1), rn(N, seed=2), rn(M, N, seed=3)
+    outs = []
+    for _ in range(2):
+        C = torch.empty(M, N, device=DEV)
+        Z = torch.empty(M, N, device=DEV)
+        GF.gemm(A, B, C, M, N, K, lda=M, ldb=N, ldc=N, transA=True, alpha=0.5, bias=bias, act=2, zout=Z, ldz=N,
+                residual=R, ldr=N, rscale=-1.0, ksplit=ksplit)
+        outs.append(C)
+    z = 0.5 * A.double().t() @ B.double() + bias.double()
+    assert rel_l2(Z, z) < TF32_TOL
+    assert rel_l2(outs[0], R.double() - torch.nn.functional.silu(z)) < TF32_TOL
+    assert torch.equal(outs[0], outs[1])             # fixed-order split-K reduction
+
+
+@pytest.mark.parametrize("act", ["silu", "relu"])
+def test_linear_autograd_tensor_cores(act):
+    """TF32 forward <= 2e-3, gradients <= 5e-3.  For ReLU the reference gate is taken from the
+    kernel's own output: a TF32-perturbed pre-activation flips the sign of ~4e-4 of the entries
+    near zero, which alone moves gradients by sqrt(4e-4) ~ 2e-2 in any reduced-precision
+    implementation (cuBLAS TF32 included) and says nothing about the kernel."""
+    GF.set_precision("tf32")
+    x = rn(8, 1849, 128).requires_grad_(True)
+    W = (0.1 * rn(256, 128, seed=1)).requires_grad_(True)
+    b = rn(256, seed=2).requires_grad_(True)
+    y = GF.linear(x, W, b, act=act)
+    cot = rn(8, 1849, 256, seed=4)
+    grads = torch.autograd.grad((y * cot).sum(), [x, W, b])
+    xd, Wd, bd = [t.detach().double().requires_grad_(True) for t in (x, W, b)]
+    z = xd @ Wd.t() + bd
+    yr = torch.nn.functional.silu(z) if act == "silu" else z * (y.detach() > 0).double()
+    gr = torch.autograd.grad((yr * cot.double()).sum(), [xd, Wd, bd])
+    assert rel_l2(y, yr) < TF32_TOL
+    for g, r in zip(grads, gr):
+        assert rel_l2(g, r) < 5e-3
 
 
 @pytest.mark.parametrize("ksplit", [1, 3, 16])

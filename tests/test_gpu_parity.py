@@ -15,7 +15,18 @@ from test_abi_and_host import build_module
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
-FWD_TOL, GRAD_TOL = 1e-5, 1e-4
+# stated tolerances (relative L2): exact-fp32 path / tcgen05 TF32 path
+# TF32 gradients through a ReLU FFN carry sign-flip noise ~ sqrt(P(|z| < eps_tf32)) ~ 2e-2 that any
+# reduced-precision implementation has (see test_gpu_kernels.py::test_linear_autograd_tensor_cores), hence
+# grad = 3e-2 for the ReLU encoder graphs; smooth graphs are held to 5e-3 there.
+TOLS = {"fp32": dict(fwd=1e-5, grad=1e-4, model=1e-3), "tf32": dict(fwd=2e-3, grad=3e-2, model=3e-2)}
+
+
+@pytest.fixture(params=["fp32", "tf32"], autouse=True)
+def precision(request):
+    G.set_precision(request.param)
+    yield request.param
+    G.set_precision("tf32")
 # the stock cuDNN convolutions of the (out-of-scope) scalers default to TF32; parity is fp32
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
@@ -27,6 +38,24 @@ def zero_dropouts(mod):
         if isinstance(m, torch.nn.Dropout):
             m.p = 0.0
     return mod
+
+
+def eager_tf32_errors(fix):
+    """Yardstick for the TF32 path: the oracle (plain eager PyTorch) on the GPU with cuBLAS TF32
+    matmuls enabled -- what the reference itself computes on an Ampere+ GPU with PyTorch 1.9's
+    defaults -- measured against the recorded fp32 reference outputs/gradients."""
+    from helpers import oracle_grads
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        outs, gi, gp = oracle_grads(fix, dtype=torch.float32, device=DEV)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = False
+    err = {"out": rel_l2(outs[0], fix["outputs"][0])}
+    for k, ref in fix["grad_inputs"].items():
+        err[k] = rel_l2(gi[k], ref)
+    for k, ref in fix["grad_params"].items():
+        err[k] = rel_l2(gp[k], ref)
+    return err
 
 
 def run_module(fix, mod, inputs):
@@ -45,7 +74,10 @@ def run_module(fix, mod, inputs):
 
 
 @pytest.mark.parametrize("name", golden_names())
-def test_cuda_path_matches_reference_fixture(name):
+def test_cuda_path_matches_reference_fixture(name, precision):
+    FWD_TOL, GRAD_TOL = TOLS[precision]["fwd"], TOLS[precision]["grad"]
+    if name.startswith("model_"):
+        FWD_TOL, GRAD_TOL = max(FWD_TOL, TOLS[precision]["model"] / 10), TOLS[precision]["model"]
     fix = load_golden(name)
     mod = build_module(fix)
     mod.load_state_dict(fix["state_dict"])
@@ -70,7 +102,9 @@ def test_cuda_path_matches_reference_fixture(name):
         assert rel_l2(outs[0], refs[0]) < FWD_TOL
         assert rel_l2(torch.view_as_real(outs[1]), refs[1]) < FWD_TOL
         return
-    assert rel_l2(outs[0], refs[0]) < FWD_TOL, rel_l2(outs[0], refs[0])
+    # TF32 mode: never worse than 3x eager PyTorch with cuBLAS-TF32 on the same graph
+    yard = eager_tf32_errors(fix) if precision == "tf32" else {}
+    assert rel_l2(outs[0], refs[0]) < max(FWD_TOL, 3 * yard.get("out", 0.0)), (rel_l2(outs[0], refs[0]), yard.get("out"))
     if name.startswith("attn_galerkin"):
         assert rel_l2(outs[1], refs[1]) < FWD_TOL          # returned attention matrix
     gnames = list(fix["grad_inputs"])
@@ -80,7 +114,7 @@ def test_cuda_path_matches_reference_fixture(name):
                                 [inputs[k] for k in gnames] + [params[k] for k in pnames])
     for k, g in zip(gnames + pnames, grads):
         ref = fix["grad_inputs"].get(k, fix["grad_params"].get(k))
-        assert rel_l2(g, ref) < GRAD_TOL, (k, rel_l2(g, ref))
+        assert rel_l2(g, ref) < max(GRAD_TOL, 3 * yard.get(k, 0.0)), (k, rel_l2(g, ref), yard.get(k))
 
 
 def _mesh(b, n, dev):
@@ -108,7 +142,8 @@ def _perturb(mod, seed=0):
     (dict(d_model=48, n_head=1, pos_dim=2, dim_feedforward=96, attention_type="galerkin",
           layer_norm=True, attn_norm=False, dropout=0.0, ffn_dropout=0.0), 4, 4096),
 ])
-def test_encoder_layer_matches_oracle_at_baseline_sizes(cfg, B, n):
+def test_encoder_layer_matches_oracle_at_baseline_sizes(cfg, B, n, precision):
+    FWD_TOL, GRAD_TOL = TOLS[precision]["fwd"], TOLS[precision]["grad"]
     torch.manual_seed(1)
     mod = G.SimpleTransformerEncoderLayer(**cfg)
     _perturb(mod)
@@ -146,11 +181,11 @@ def test_attention_linearity_and_mask_semantics_at_full_size():
         mask = (torch.rand_like(A0) > 0.5).to(torch.uint8)
         a.set_attn_mask(mask)
         _, A1 = a(x, x, x, pos=pos)
-        assert rel_l2(A1, A0 * 2 * mask) < 1e-6
+        assert rel_l2(A1, A0 * 2 * mask) < 1e-6        # same projections, same kernels: only the mask differs
         # Q-linearity of the head outputs for fixed K, V: heads(q1 + q2) = heads(q1) + heads(q2) - heads(0)
         q1, q2 = torch.randn_like(x), torch.randn_like(x)
         h = lambda q: a.forward_heads(q, x, x, pos=pos)[0]
-        assert rel_l2(h(q1 + q2) + h(torch.zeros_like(x)), h(q1) + h(q2)) < 1e-5
+        assert rel_l2(h(q1 + q2) + h(torch.zeros_like(x)), h(q1) + h(q2)) < (1e-5 if G.get_precision() == "fp32" else 2e-3)
 
 
 def test_reference_dropout_statistics():
@@ -169,7 +204,7 @@ def test_reference_dropout_statistics():
     assert rel_l2(A1[kept], 2 * A0[kept]) < 1e-6
 
 
-def test_full_model_c3_matches_oracle():
+def test_full_model_c3_matches_oracle(precision):
     """FourierTransformer2D at the BASELINE C3 configuration (141^2 fine, 43^2 coarse, d_model 128,
     4 heads, 10 layers, 2 SpectralConv2d) against the fp64 oracle, forward loss and input gradient."""
     torch.manual_seed(4)
@@ -193,8 +228,62 @@ def test_full_model_c3_matches_oracle():
     l32 = ((O.fourier_transformer_2d(sd32, cfg, n32, pos, grid) - target) ** 2).mean()
     g32, = torch.autograd.grad(l32, n32)
     eager_err = rel_l2(g32, gref)
+    if precision == "tf32":
+        # yardstick: the same graph in eager PyTorch with cuBLAS TF32 matmuls (and fp32 convs)
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            nt = node.detach().clone().requires_grad_(True)
+            lt = ((O.fourier_transformer_2d(sd32, cfg, nt, pos, grid) - target) ** 2).mean()
+            gt, = torch.autograd.grad(lt, nt)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = False
+        loss_yard = abs(lt.item() - ref.item()) / abs(ref.item())
+        grad_yard = rel_l2(gt, gref)
+        mine = (abs(loss.item() - ref.item()) / abs(ref.item()), rel_l2(gnode, gref))
+        print(f"C3 TF32: loss rel {mine[0]:.2e} (eager-tf32 {loss_yard:.2e}); dnode rel {mine[1]:.2e} "
+              f"(eager-tf32 {grad_yard:.2e}, eager-fp32 {eager_err:.2e})")
+        assert mine[0] < max(1e-3, 3 * loss_yard), (mine, loss_yard)
+        assert mine[1] < max(3e-2, 3 * grad_yard), (mine, grad_yard)
+        return
     assert abs(loss.item() - ref.item()) / abs(ref.item()) < 1e-4
     # stated tolerance for the 10-layer end-to-end gradient: 1e-2, and never worse than 3x what
     # fp32 eager PyTorch itself achieves on the same graph
     assert rel_l2(gnode, gref) < max(1e-3, 3 * eager_err), (rel_l2(gnode, gref), eager_err)
     assert rel_l2(gnode, gref) < 1e-2
+
+
+def test_graphed_step_matches_eager_and_refreshes_dropout():
+    """CUDA-graph replay of fwd+bwd: same loss/grads as eager with dropout off; with the config's
+    dropouts on, consecutive replays draw different masks (device-side seed counter)."""
+    from galerkin_transformer_b200.graphs import GraphedStep
+    from bench import c3_config, c3_inputs
+    G.set_precision("tf32")
+    torch.manual_seed(5)
+    cfg = c3_config(dropout_free=True)
+    cfg["num_encoder_layers"] = 2
+    model = G.FourierTransformer2D(**cfg).to(DEV)
+    G.set_attn_dropout(model, "off")
+    data = c3_inputs(2, DEV)
+
+    def loss_fn(n_, p_, g_, t_):
+        return ((model(n_, None, p_, g_)["preds"] - t_) ** 2).mean()
+
+    eager = loss_fn(*data)
+    eager.backward()
+    ref = [p.grad.clone() for p in model.parameters()]
+    graphed = GraphedStep(loss_fn, data, model.parameters())
+    for _ in range(2):
+        l = graphed(*data)
+        assert abs(l.item() - eager.item()) < 1e-6 * abs(eager.item()) + 1e-9
+        for g, r in zip(graphed.static_grads, ref):
+            # our kernels are run-to-run deterministic; the stock cuDNN wgrad of the scalers is not bitwise
+            assert torch.allclose(g, r, rtol=1e-4, atol=1e-9)
+    # dropout on: replays must differ from each other
+    cfg2 = c3_config()
+    cfg2["num_encoder_layers"] = 2
+    m2 = G.FourierTransformer2D(**cfg2).to(DEV)
+    g2 = GraphedStep(lambda n_, p_, g_, t_: ((m2(n_, None, p_, g_)["preds"] - t_) ** 2).mean(), data,
+                     m2.parameters())
+    a = g2(*data).item()
+    b = g2(*data).item()
+    assert a != b
