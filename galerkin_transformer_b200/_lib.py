@@ -52,16 +52,16 @@ SIGNATURES = {
     "gb200_layernorm_bwd_workspace_bytes": (c_sz, [c_ll, c_int]),
     "gb200_layernorm_bwd": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_vp, c_vp, c_vp,
                                     c_int, c_vp, c_sz, c_vp]),
-    "gb200_headnorm_fwd": (c_int, [c_int, c_vp, c_int, c_int, c_ll, c_int, c_int, c_float, c_vp, c_vp]),
+    "gb200_headnorm_fwd": (c_int, [c_int, c_vp, c_int, c_int, c_int, c_ll, c_int, c_int, c_float, c_vp, c_vp, c_vp]),
     "gb200_headnorm_bwd_workspace_bytes": (c_sz, [c_ll, c_int, c_int]),
-    "gb200_headnorm_bwd": (c_int, [c_int, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_ll, c_int,
-                                   c_int, c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),
+    "gb200_headnorm_bwd": (c_int, [c_int, c_vp, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp,
+                                   c_vp, c_ll, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),
     "gb200_attn_suggest_nsplit": (c_int, [c_int] * 3),
     "gb200_attn_xty_workspace_bytes": (c_sz, [c_int] * 4),
     "gb200_attn_xty": (c_int, [c_int, _HOP, _HOP, c_vp, c_int, c_int, c_int, c_int, c_int, c_float, c_vp,
-                               c_vp, c_int, c_vp, c_sz, c_vp]),
+                               c_vp, c_int, c_vp, c_sz, c_int, c_vp]),
     "gb200_attn_xm": (c_int, [c_int, _HOP, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp,
-                              c_int, c_int, c_int, c_float, c_vp]),
+                              c_int, c_int, c_int, c_float, c_int, c_vp]),
     "gb200_spectral_suggest_ysplit": (c_int, [c_ll, c_int, c_int]),
     "gb200_spectral_ydft_workspace_bytes": (c_sz, [c_ll, c_int, c_int, c_int]),
     "gb200_spectral_ydft": (c_int, [c_int, c_vp, c_ll, c_int, c_int, c_int, c_vp, c_float, c_int, c_vp,

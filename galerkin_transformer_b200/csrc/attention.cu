@@ -37,6 +37,10 @@ __device__ __forceinline__ float load_aug(const HeadOperand& op, const float* __
     return v;
 }
 
+}  // namespace gb200
+#include "attention_mma.cuh"
+namespace gb200 {
+
 // -------------------------------------------------------------------------------------------
 // per-head LayerNorm, forward: x -> xhat (in place), rstd (T, H) saved for backward.
 // One CTA stages ROWS token rows (all heads) through shared memory with coalesced loads,
@@ -126,6 +130,111 @@ __global__ void headnorm_bwd_kernel(float* __restrict__ dy, int lddy, int dcol0,
         dy[(t0 + r) * lddy + dcol0 + c] = sdy[r * WS + c];
     }
 }
+
+// -------------------------------------------------------------------------------------------
+// Coalesced variants (d_k/4 a power of two <= 32 and 256 % (H*d_k/4) == 0): one float4 per lane, the
+// d_k/4 lanes of a head group combine their statistics with warp shuffles; no shared-memory staging.
+// blockIdx.y selects the operand block (K and V, or Q and K, normalised by ONE launch).
+// -------------------------------------------------------------------------------------------
+struct HeadNormBlocks {
+    int col0[2];
+    float* rstd[2];
+    const float* gamma[2];
+    float* part[2];
+    int dcol0[2];
+};
+
+template <int LG>   // lanes per head group = d_k / 4
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = LG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int LG>
+__global__ void __launch_bounds__(256) headnorm_fwd_vec_kernel(float* __restrict__ x, int ld, HeadNormBlocks blk,
+                                                               long long T, int H, int dk, float eps) {
+    const int col0 = blk.col0[blockIdx.y];
+    float* rstd_out = blk.rstd[blockIdx.y];
+    const int rowq = H * LG;                              // float4s per row
+    const int q = threadIdx.x % rowq, rsub = threadIdx.x / rowq, rpb = 256 / rowq;
+    const float inv = 1.f / dk;
+    // uniform trip count: every lane of a warp takes part in every shuffle (rows past T are predicated)
+    const long long stride = (long long)gridDim.x * rpb;
+    const long long iters = (T + stride - 1) / stride;
+    for (long long it = 0; it < iters; ++it) {
+        const long long r = (long long)blockIdx.x * rpb + rsub + it * stride;
+        const bool ok = r < T;
+        float4* p = reinterpret_cast<float4*>(x + (ok ? r : 0) * ld + col0) + q;
+        float4 v = ok ? *p : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float mean = group_sum<LG>(v.x + v.y + v.z + v.w) * inv;
+        v.x -= mean; v.y -= mean; v.z -= mean; v.w -= mean;
+        const float var = group_sum<LG>(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w) * inv;
+        const float rs = rsqrtf(var + eps);
+        if (ok) {
+            *p = make_float4(v.x * rs, v.y * rs, v.z * rs, v.w * rs);
+            if (q % LG == 0) rstd_out[r * H + q / LG] = rs;
+        }
+    }
+}
+
+template <int LG>
+__global__ void __launch_bounds__(256) headnorm_bwd_vec_kernel(float* __restrict__ dy, int lddy,
+                                                               const float* __restrict__ xhat, int ldx,
+                                                               HeadNormBlocks blk, long long T, int H, int dk) {
+    __shared__ float4 sg[256], sb[256];
+    const int bi = blockIdx.y;
+    const int rowq = H * LG;
+    const int q = threadIdx.x % rowq, rsub = threadIdx.x / rowq, rpb = 256 / rowq;
+    const float inv = 1.f / dk;
+    const float4 gm = reinterpret_cast<const float4*>(blk.gamma[bi])[q];
+    const float* rstd = blk.rstd[bi];
+    float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag;
+    const long long stride = (long long)gridDim.x * rpb;
+    const long long iters = (T + stride - 1) / stride;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long it = 0; it < iters; ++it) {
+        const long long r = (long long)blockIdx.x * rpb + rsub + it * stride;
+        const bool ok = r < T;
+        float4* dp = reinterpret_cast<float4*>(dy + (ok ? r : 0) * lddy + blk.dcol0[bi]) + q;
+        const float4 d = ok ? *dp : zero4;
+        const float4 xh = ok ? *(reinterpret_cast<const float4*>(xhat + r * ldx + blk.col0[bi]) + q) : zero4;
+        ag.x += d.x * xh.x; ag.y += d.y * xh.y; ag.z += d.z * xh.z; ag.w += d.w * xh.w;
+        ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
+        const float4 gd = make_float4(gm.x * d.x, gm.y * d.y, gm.z * d.z, gm.w * d.w);
+        const float c1 = group_sum<LG>(gd.x + gd.y + gd.z + gd.w) * inv;
+        const float c2 = group_sum<LG>(gd.x * xh.x + gd.y * xh.y + gd.z * xh.z + gd.w * xh.w) * inv;
+        const float rs = ok ? rstd[r * H + q / LG] : 0.f;
+        if (ok) *dp = make_float4(rs * (gd.x - c1 - xh.x * c2), rs * (gd.y - c1 - xh.y * c2), rs * (gd.z - c1 - xh.z * c2),
+                          rs * (gd.w - c1 - xh.w * c2));
+    }
+    // fixed-order sum over the rpb row-threads that share a column quad, then the CTA partial
+    sg[threadIdx.x] = ag; sb[threadIdx.x] = ab;
+    __syncthreads();
+    if (threadIdx.x < rowq) {
+        float4 tg = sg[threadIdx.x], tb = sb[threadIdx.x];
+        for (int k = 1; k < rpb; ++k) {
+            const float4 a = sg[threadIdx.x + k * rowq], b2 = sb[threadIdx.x + k * rowq];
+            tg.x += a.x; tg.y += a.y; tg.z += a.z; tg.w += a.w;
+            tb.x += b2.x; tb.y += b2.y; tb.z += b2.z; tb.w += b2.w;
+        }
+        float* part = blk.part[bi];
+        const int W = H * dk;
+        reinterpret_cast<float4*>(part + ((long long)blockIdx.x * 2 + 0) * W)[threadIdx.x] = tg;
+        reinterpret_cast<float4*>(part + ((long long)blockIdx.x * 2 + 1) * W)[threadIdx.x] = tb;
+    }
+}
+
+static int headnorm_vec_lanes(int H, int dk, int ld, int col0, const void* base) {
+    if (dk % 4) return 0;
+    const int lg = dk / 4;
+    if (lg < 1 || lg > 32 || (lg & (lg - 1))) return 0;
+    const int rowq = H * lg;
+    if (rowq > 256 || 256 % rowq) return 0;
+    if ((ld % 4) || (col0 % 4) || ((uintptr_t)base % 16)) return 0;
+    return lg;
+}
+constexpr int HN_VEC_BLOCKS = 296;
 
 // out[j][c] (+)= sum_blocks part[blk][j][c]   (j = 0: dgamma, 1: dbeta), fixed order
 __global__ void headnorm_bwd_reduce_kernel(const float* __restrict__ part, int nblocks, int W,
@@ -293,48 +402,108 @@ static HeadOperand make_op(const gb200_head_operand* o) {
     return h;
 }
 
-extern "C" int gb200_headnorm_fwd(int device, float* x, int ld, int col0, long long T, int H, int dk, float eps,
-                                  float* rstd, void* stream) {
+extern "C" int gb200_headnorm_fwd(int device, float* x, int ld, int col0, int col0b, long long T, int H, int dk,
+                                  float eps, float* rstd, float* rstd_b, void* stream) {
     use_device(device);
     GB_REQUIRE(x && rstd && T >= 0 && H >= 1 && dk >= 1, "gb200_headnorm_fwd: bad arguments");
+    GB_REQUIRE(col0b < 0 || rstd_b, "gb200_headnorm_fwd: second block needs its own rstd buffer");
     if (T == 0) return GB200_OK;
+    cudaStream_t st = as_stream(stream);
+    const int nblk = col0b >= 0 ? 2 : 1;
+    int lg = headnorm_vec_lanes(H, dk, ld, col0, x);
+    if (lg && nblk == 2 && !headnorm_vec_lanes(H, dk, ld, col0b, x)) lg = 0;
+    if (lg) {
+        HeadNormBlocks blk = {};
+        blk.col0[0] = col0; blk.col0[1] = col0b; blk.rstd[0] = rstd; blk.rstd[1] = rstd_b;
+        const int rpb = 256 / (H * lg);
+        int blocks = cdiv(T, rpb);
+        if (blocks > HN_VEC_BLOCKS) blocks = HN_VEC_BLOCKS;
+        dim3 grid(blocks, nblk);
+#define HN_FWD(LG) headnorm_fwd_vec_kernel<LG><<<grid, 256, 0, st>>>(x, ld, blk, T, H, dk, eps)
+        switch (lg) { case 1: HN_FWD(1); break; case 2: HN_FWD(2); break; case 4: HN_FWD(4); break;
+                      case 8: HN_FWD(8); break; case 16: HN_FWD(16); break; default: HN_FWD(32); }
+#undef HN_FWD
+        return check_launch("gb200_headnorm_fwd");
+    }
     size_t smem = (size_t)HN_ROWS * (H * dk + 1) * sizeof(float);
     GB_REQUIRE(smem <= 200 * 1024, "gb200_headnorm_fwd: H*d_k=%d too wide", H * dk);
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(headnorm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    headnorm_fwd_kernel<<<cdiv(T, HN_ROWS), 256, smem, as_stream(stream)>>>(x, ld, col0, T, H, dk, eps, rstd);
-    return check_launch("gb200_headnorm_fwd");
+    headnorm_fwd_kernel<<<cdiv(T, HN_ROWS), 256, smem, st>>>(x, ld, col0, T, H, dk, eps, rstd);
+    if (nblk == 2) headnorm_fwd_kernel<<<cdiv(T, HN_ROWS), 256, smem, st>>>(x, ld, col0b, T, H, dk, eps, rstd_b);
+    return check_launch("gb200_headnorm_fwd", nblk);
 }
 
 extern "C" size_t gb200_headnorm_bwd_workspace_bytes(long long T, int H, int dk) {
-    return (size_t)cdiv(T, HN_ROWS) * 2 * H * dk * sizeof(float);
+    long long nb = cdiv(T, HN_ROWS);
+    if (nb < HN_VEC_BLOCKS) nb = HN_VEC_BLOCKS;
+    return (size_t)2 * nb * 2 * H * dk * sizeof(float);          // room for two operand blocks
 }
 
-extern "C" int gb200_headnorm_bwd(int device, float* dy, int lddy, int dcol0, const float* xhat, int ldx,
-                                  int xcol0, const float* rstd, const float* gamma, long long T, int H, int dk,
-                                  float* dgamma, float* dbeta, int accumulate, float* workspace,
+extern "C" int gb200_headnorm_bwd(int device, float* dy, int lddy, int dcol0, int dcol0b, const float* xhat, int ldx,
+                                  int xcol0, int xcol0b, const float* rstd, const float* rstd_b, const float* gamma,
+                                  const float* gamma_b, long long T, int H, int dk, float* dgamma, float* dbeta,
+                                  float* dgamma_b, float* dbeta_b, int accumulate, float* workspace,
                                   size_t workspace_bytes, void* stream) {
     use_device(device);
     GB_REQUIRE(dy && xhat && rstd && gamma && dgamma && dbeta, "gb200_headnorm_bwd: null argument");
+    const int nblk = dcol0b >= 0 ? 2 : 1;
+    GB_REQUIRE(nblk == 1 || (rstd_b && gamma_b && dgamma_b && dbeta_b && xcol0b >= 0),
+               "gb200_headnorm_bwd: second block is incomplete");
     if (T == 0) return GB200_OK;
     GB_REQUIRE(workspace && workspace_bytes >= gb200_headnorm_bwd_workspace_bytes(T, H, dk),
                "gb200_headnorm_bwd: workspace too small");
-    size_t smem = (size_t)2 * HN_ROWS * (H * dk + 1) * sizeof(float);
-    GB_REQUIRE(smem <= 200 * 1024, "gb200_headnorm_bwd: H*d_k=%d too wide", H * dk);
+    cudaStream_t st = as_stream(stream);
+    const int W = H * dk;
+    int lg = headnorm_vec_lanes(H, dk, lddy, dcol0, dy);
+    if (lg && (!headnorm_vec_lanes(H, dk, ldx, xcol0, xhat) || ((uintptr_t)gamma % 16))) lg = 0;
+    if (lg && nblk == 2 && (!headnorm_vec_lanes(H, dk, lddy, dcol0b, dy) || !headnorm_vec_lanes(H, dk, ldx, xcol0b, xhat) ||
+                            ((uintptr_t)gamma_b % 16)))
+        lg = 0;
+    float* part_a = workspace;
+    if (lg) {
+        const int rpb = 256 / (H * lg);
+        int blocks = cdiv(T, rpb);
+        if (blocks > HN_VEC_BLOCKS) blocks = HN_VEC_BLOCKS;
+        float* part_b = workspace + (size_t)blocks * 2 * W;
+        HeadNormBlocks blk = {};
+        blk.col0[0] = xcol0; blk.col0[1] = xcol0b; blk.dcol0[0] = dcol0; blk.dcol0[1] = dcol0b;
+        blk.rstd[0] = const_cast<float*>(rstd); blk.rstd[1] = const_cast<float*>(rstd_b);
+        blk.gamma[0] = gamma; blk.gamma[1] = gamma_b; blk.part[0] = part_a; blk.part[1] = part_b;
+        dim3 grid(blocks, nblk);
+#define HN_BWD(LG) headnorm_bwd_vec_kernel<LG><<<grid, 256, 0, st>>>(dy, lddy, xhat, ldx, blk, T, H, dk)
+        switch (lg) { case 1: HN_BWD(1); break; case 2: HN_BWD(2); break; case 4: HN_BWD(4); break;
+                      case 8: HN_BWD(8); break; case 16: HN_BWD(16); break; default: HN_BWD(32); }
+#undef HN_BWD
+        headnorm_bwd_reduce_kernel<<<dim3(cdiv(W, 32), 2), dim3(32, 32), 0, st>>>(part_a, blocks, W, dgamma, dbeta,
+                                                                                accumulate);
+        if (nblk == 2)
+            headnorm_bwd_reduce_kernel<<<dim3(cdiv(W, 32), 2), dim3(32, 32), 0, st>>>(part_b, blocks, W, dgamma_b,
+                                                                                    dbeta_b, accumulate);
+        return check_launch("gb200_headnorm_bwd", 1 + nblk);
+    }
+    size_t smem = (size_t)2 * HN_ROWS * (W + 1) * sizeof(float);
+    GB_REQUIRE(smem <= 200 * 1024, "gb200_headnorm_bwd: H*d_k=%d too wide", W);
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(headnorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int nblocks = cdiv(T, HN_ROWS);
-    cudaStream_t st = as_stream(stream);
-    headnorm_bwd_kernel<<<nblocks, 256, smem, st>>>(dy, lddy, dcol0, xhat, ldx, xcol0, rstd, gamma, T, H, dk,
-                                                   workspace);
-    headnorm_bwd_reduce_kernel<<<dim3(cdiv(H * dk, 32), 2), dim3(32, 8), 0, st>>>(workspace, nblocks, H * dk, dgamma,
-                                                                                dbeta, accumulate);
-    return check_launch("gb200_headnorm_bwd", 2);
+    const int nblocks = cdiv(T, HN_ROWS);
+    float* part_b = workspace + (size_t)nblocks * 2 * W;
+    headnorm_bwd_kernel<<<nblocks, 256, smem, st>>>(dy, lddy, dcol0, xhat, ldx, xcol0, rstd, gamma, T, H, dk, part_a);
+    headnorm_bwd_reduce_kernel<<<dim3(cdiv(W, 32), 2), dim3(32, 32), 0, st>>>(part_a, nblocks, W, dgamma, dbeta,
+                                                                            accumulate);
+    if (nblk == 2) {
+        headnorm_bwd_kernel<<<nblocks, 256, smem, st>>>(dy, lddy, dcol0b, xhat, ldx, xcol0b, rstd_b, gamma_b, T, H, dk,
+                                                        part_b);
+        headnorm_bwd_reduce_kernel<<<dim3(cdiv(W, 32), 2), dim3(32, 32), 0, st>>>(part_b, nblocks, W, dgamma_b,
+                                                                                dbeta_b, accumulate);
+    }
+    return check_launch("gb200_headnorm_bwd", 2 * nblk);
 }
 
 extern "C" int gb200_attn_suggest_nsplit(int B, int H, int n) {
     int bh = B * H;
-    int want = (3 * 148 + bh - 1) / bh;
+    int want = (2 * 148) / bh;          // one wave at two resident CTAs per SM
+    if (want < 1) want = 1;
     int maxs = (n + 63) / 64;
     int s = want < maxs ? want : maxs;
     return s < 1 ? 1 : s;
@@ -347,7 +516,7 @@ extern "C" size_t gb200_attn_xty_workspace_bytes(int B, int H, int d, int nsplit
 extern "C" int gb200_attn_xty(int device, const gb200_head_operand* L, const gb200_head_operand* R,
                               const float* pos, int B, int H, int n, int dk, int p, float scale,
                               const unsigned char* keep_mask, float* out, int nsplit, float* workspace,
-                              size_t workspace_bytes, void* stream) {
+                              size_t workspace_bytes, int tensor_cores, void* stream) {
     use_device(device);
     GB_REQUIRE(L && R && out && L->ptr && R->ptr, "gb200_attn_xty: null operand");
     GB_REQUIRE(B >= 1 && H >= 1 && n >= 1 && dk >= 1 && p >= 0, "gb200_attn_xty: bad shape");
@@ -362,6 +531,12 @@ extern "C" int gb200_attn_xty(int device, const gb200_head_operand* L, const gb2
     dim3 grid(nsplit, B * H);
     cudaStream_t st = as_stream(stream);
     HeadOperand l = make_op(L), r = make_op(R);
+    if (tensor_cores && d <= 64) {       // warp-level TF32 MMA, tiles right-sized to d
+        if (d <= 24) xty_mma_kernel<2, 3><<<grid, 256, 0, st>>>(l, r, pos, p, dk, H, n, nsplit, chunk, workspace);
+        else if (d <= 40) xty_mma_kernel<3, 5><<<grid, 256, 0, st>>>(l, r, pos, p, dk, H, n, nsplit, chunk, workspace);
+        else if (d <= 56) xty_mma_kernel<4, 7><<<grid, 256, 0, st>>>(l, r, pos, p, dk, H, n, nsplit, chunk, workspace);
+        else xty_mma_kernel<4, 8><<<grid, 256, 0, st>>>(l, r, pos, p, dk, H, n, nsplit, chunk, workspace);
+    } else
     if (dp == 32) xty_kernel<32><<<grid, 256, 0, st>>>(l, r, pos, p, dk, H, n, nsplit, chunk, workspace);
     else if (dp == 64) xty_kernel<64><<<grid, 256, 0, st>>>(l, r, pos, p, dk, H, n, nsplit, chunk, workspace);
     else xty_kernel<128><<<grid, 256, 0, st>>>(l, r, pos, p, dk, H, n, nsplit, chunk, workspace);
@@ -374,7 +549,7 @@ extern "C" int gb200_attn_xty(int device, const gb200_head_operand* L, const gb2
 
 extern "C" int gb200_attn_xm(int device, const gb200_head_operand* L, const float* pos, const float* M,
                              int transM, int B, int H, int n, int dk, int p, float* out, int ldo, int ocol0,
-                             int out_augmented, float out_scale, void* stream) {
+                             int out_augmented, float out_scale, int tensor_cores, void* stream) {
     use_device(device);
     GB_REQUIRE(L && L->ptr && M && out, "gb200_attn_xm: null operand");
     GB_REQUIRE(p == 0 || pos || L->augmented, "gb200_attn_xm: pos is null but pos_dim=%d", p);
@@ -385,6 +560,17 @@ extern "C" int gb200_attn_xm(int device, const gb200_head_operand* L, const floa
     size_t smem = (size_t)(dp + 64) * (dp + 1) * sizeof(float);
     cudaStream_t st = as_stream(stream);
     HeadOperand l = make_op(L);
+    if (tensor_cores && d <= 64) {
+#define LAUNCH_XMM(KT, NT, TT)                                                                               \
+    xm_mma_kernel<KT, NT, TT><<<dim3(cdiv(n, TT), B * H), TT * 2, 0, st>>>(l, pos, M, transM, p, dk, H, n, out, ldo, \
+                                                                           ocol0, out_augmented, out_scale)
+        if (d <= 24) LAUNCH_XMM(3, 3, 128);
+        else if (d <= 40) LAUNCH_XMM(5, 5, 128);
+        else if (d <= 56) LAUNCH_XMM(7, 7, 64);
+        else LAUNCH_XMM(8, 8, 64);
+#undef LAUNCH_XMM
+        return check_launch("gb200_attn_xm");
+    }
 #define LAUNCH_XM(DPV)                                                                                  \
     do {                                                                                                \
         if (smem > 48 * 1024)                                                                           \

@@ -73,22 +73,22 @@ __device__ __forceinline__ float dropout_scale(float p, uint64_t seed, uint64_t 
     return uf < p ? 0.f : 1.f / (1.f - p);
 }
 
-// out[c] (+)= scale * sum_{p < nparts} part[p * stride + c]   for c < width: a (32 x 8)-thread CTA per 32
+// out[c] (+)= scale * sum_{p < nparts} part[p * stride + c]   for c < width: a (32 x 32)-thread CTA per 32
 // columns, rows strided over threadIdx.y, fixed-order shared-memory finish (deterministic).
 __device__ __forceinline__ void reduce_partials_2d(const float* __restrict__ part, int nparts, long long stride,
                                                    int width, float scale, int accumulate,
                                                    float* __restrict__ out) {
-    __shared__ float red[8][33];
+    __shared__ float red[32][33];
     const int c = blockIdx.x * 32 + threadIdx.x;
     float s = 0.f;
     if (c < width)
-        for (int p = threadIdx.y; p < nparts; p += 8) s += part[(long long)p * stride + c];
+        for (int p = threadIdx.y; p < nparts; p += 32) s += part[(long long)p * stride + c];
     red[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
     if (threadIdx.y == 0 && c < width) {
         float t = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+        for (int i = 0; i < 32; ++i) t += red[i][threadIdx.x];
         t *= scale;
         out[c] = accumulate ? out[c] + t : t;
     }

@@ -146,7 +146,7 @@ __global__ void colsum_partial_kernel(const float* __restrict__ X, int M, int N,
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     const int r0 = blockIdx.y * rows_per_block;
     const int r1 = min(M, r0 + rows_per_block);
-    __shared__ float red[8][33];
+    __shared__ float red[32][33];
     float s = 0.f;
     if (n < N)
         for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) s += X[(long long)r * ld + n];
@@ -154,7 +154,8 @@ __global__ void colsum_partial_kernel(const float* __restrict__ X, int M, int N,
     __syncthreads();
     if (threadIdx.y == 0 && n < N) {
         float t = 0.f;
-        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) t += red[i][threadIdx.x];
         part[(long long)blockIdx.y * N + n] = t;
     }
 }
@@ -184,6 +185,33 @@ __global__ void epilogue_bwd_kernel(const float* __restrict__ dy, int lddy, cons
             v *= act_grad(ACT_SILU, z[m * ldz + n]);
         }
         gout[m * ldg + n] = v;
+    }
+}
+
+// float4 variant: contiguous rows (ld == N), N % 4 == 0, 16-byte aligned pointers; 32-bit indexing
+template <int ACT>
+__global__ void epilogue_bwd_vec4_kernel(const float4* __restrict__ dy, const float4* __restrict__ ref,
+                                         float4* __restrict__ gout, unsigned int total4, float rscale, float drop_p,
+                                         unsigned long long seed, const unsigned long long* seed_off) {
+    if (drop_p > 0.f && seed_off) seed += *seed_off;
+    for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < total4; e += gridDim.x * blockDim.x) {
+        float4 v = dy[e];
+        v.x *= rscale; v.y *= rscale; v.z *= rscale; v.w *= rscale;
+        if (drop_p > 0.f) {
+            const unsigned long long b = (unsigned long long)e * 4;
+            v.x *= dropout_scale(drop_p, seed, b);     v.y *= dropout_scale(drop_p, seed, b + 1);
+            v.z *= dropout_scale(drop_p, seed, b + 2); v.w *= dropout_scale(drop_p, seed, b + 3);
+        }
+        if (ACT == ACT_RELU) {
+            const float4 r = ref[e];
+            v.x = r.x > 0.f ? v.x : 0.f; v.y = r.y > 0.f ? v.y : 0.f;
+            v.z = r.z > 0.f ? v.z : 0.f; v.w = r.w > 0.f ? v.w : 0.f;
+        } else if (ACT == ACT_SILU) {
+            const float4 r = ref[e];
+            v.x *= act_grad(ACT_SILU, r.x); v.y *= act_grad(ACT_SILU, r.y);
+            v.z *= act_grad(ACT_SILU, r.z); v.w *= act_grad(ACT_SILU, r.w);
+        }
+        gout[e] = v;
     }
 }
 
@@ -252,7 +280,7 @@ extern "C" int gb200_gemm(int device, const float* A, int lda, int transA, const
 }
 
 extern "C" size_t gb200_colsum_workspace_bytes(long long M, int N) {
-    int rows_per_block = 256;
+    int rows_per_block = 128;
     return (size_t)cdiv(M, rows_per_block) * N * sizeof(float);
 }
 
@@ -261,15 +289,15 @@ extern "C" int gb200_colsum(int device, const float* X, int ld, long long M, int
                             void* stream) {
     use_device(device);
     GB_REQUIRE(X && out && M >= 1 && N >= 1, "gb200_colsum: bad arguments");
-    const int rows_per_block = 256;
+    const int rows_per_block = 128;
     int nparts = cdiv(M, rows_per_block);
     GB_REQUIRE(workspace && workspace_bytes >= (size_t)nparts * N * sizeof(float),
                "gb200_colsum: workspace too small");
     GB_REQUIRE(nparts <= 65535, "gb200_colsum: too many rows");
     cudaStream_t st = as_stream(stream);
-    colsum_partial_kernel<<<dim3(cdiv(N, 32), nparts), dim3(32, 8), 0, st>>>(X, (int)M, N, ld, rows_per_block,
+    colsum_partial_kernel<<<dim3(cdiv(N, 32), nparts), dim3(32, 32), 0, st>>>(X, (int)M, N, ld, rows_per_block,
                                                                                workspace);
-    colsum_final_kernel<<<cdiv(N, 32), dim3(32, 8), 0, st>>>(workspace, nparts, N, scale, accumulate, out);
+    colsum_final_kernel<<<cdiv(N, 32), dim3(32, 32), 0, st>>>(workspace, nparts, N, scale, accumulate, out);
     return check_launch("gb200_colsum", 2);
 }
 
@@ -282,6 +310,26 @@ extern "C" int gb200_epilogue_bwd(int device, const float* dy, int lddy, const f
     GB_REQUIRE(act != ACT_RELU || z || y, "gb200_epilogue_bwd: ReLU backward needs z or y");
     if (M == 0) return GB200_OK;
     long long total = M * N;
+    const float* ref = z ? z : y;
+    const int ldref = z ? ldz : ldy;
+    auto al16 = [](const void* p) { return ((uintptr_t)p % 16) == 0; };
+    if (N % 4 == 0 && lddy == N && ldg == N && (act == ACT_NONE || ldref == N) && al16(dy) && al16(g) &&
+        (act == ACT_NONE || al16(ref)) && total / 4 < 0x7fffffffLL) {
+        const unsigned int total4 = (unsigned int)(total / 4);
+        int blocks = (int)((total4 + 255) / 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        const float4* d4 = reinterpret_cast<const float4*>(dy);
+        const float4* r4 = reinterpret_cast<const float4*>(ref);
+        float4* g4 = reinterpret_cast<float4*>(g);
+        cudaStream_t st = as_stream(stream);
+        if (act == ACT_RELU)
+            epilogue_bwd_vec4_kernel<ACT_RELU><<<blocks, 256, 0, st>>>(d4, r4, g4, total4, rscale, drop_p, seed, rng_offset_ptr());
+        else if (act == ACT_SILU)
+            epilogue_bwd_vec4_kernel<ACT_SILU><<<blocks, 256, 0, st>>>(d4, r4, g4, total4, rscale, drop_p, seed, rng_offset_ptr());
+        else
+            epilogue_bwd_vec4_kernel<ACT_NONE><<<blocks, 256, 0, st>>>(d4, r4, g4, total4, rscale, drop_p, seed, rng_offset_ptr());
+        return check_launch("gb200_epilogue_bwd");
+    }
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     epilogue_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(dy, lddy, z, ldz, y, ldy, g, ldg, M, N, act,

@@ -113,7 +113,7 @@ extern "C" int gb200_layernorm_bwd(int device, const float* dy, const float* x, 
         cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaStream_t st = as_stream(stream);
     layernorm_bwd_kernel<<<nblocks, LN_WARPS * 32, smem, st>>>(dy, x, mean, rstd, gamma, rows, width, dx, workspace);
-    layernorm_bwd_reduce_kernel<<<dim3(cdiv(width, 32), 2), dim3(32, 8), 0, st>>>(workspace, nblocks, width, dgamma,
+    layernorm_bwd_reduce_kernel<<<dim3(cdiv(width, 32), 2), dim3(32, 32), 0, st>>>(workspace, nblocks, width, dgamma,
                                                                                 dbeta, accumulate);
     return check_launch("gb200_layernorm_bwd", 2);
 }

@@ -30,7 +30,7 @@ __device__ __forceinline__ float herm_weight(int ky, int n) {
 constexpr int KYG = 16;   // ky handled per thread pass
 constexpr int YCH = 64;   // Y values whose twiddles are staged per step
 
-__global__ void __launch_bounds__(256) ydft_kernel(const float* __restrict__ x, long long RC, int C, int n, int m,
+__global__ void __launch_bounds__(128) ydft_kernel(const float* __restrict__ x, long long RC, int C, int n, int m,
                                                    const float2* __restrict__ twY, float scale, int hermitian,
                                                    int nsplit, int ychunk, float2* __restrict__ out,
                                                    float2* __restrict__ part) {
@@ -148,7 +148,7 @@ __global__ void xidft_kernel(const float2* __restrict__ Oft, int B, int n, int m
 // X^: (B, halves*M2, Ci) complex; W_half: (Ci, Co, M2) complex; O^: (B, halves*M2, Co) complex.
 // One thread per mode: the weight read W[i,o,:] is a contiguous run of M2 complex numbers, so
 // the 2*Ci*Co*M2 weight floats stream through exactly once, fully coalesced.
-constexpr int MIXB = 8;
+constexpr int MIXB = 2;    // batch entries per thread: small, so the grid has enough CTAs to stream W
 
 __global__ void mix_fwd_kernel(const float2* __restrict__ Xf, const float2* __restrict__ W0,
                                const float2* __restrict__ W1, int B, int halves, int M2, int Ci, int Co,
@@ -231,6 +231,7 @@ __global__ void mix_bwd_w_kernel(const float2* __restrict__ Xf, const float2* __
 // stay in shared memory; every thread produces 4 consecutive Y for one output channel so each
 // weight / coefficient read from shared memory feeds 4 (resp. 8) FMAs.
 constexpr int YT = 32;
+constexpr int XP = YT + 4;   // pitch of the transposed x tile: float4-aligned, 4-way instead of 32-way store conflicts
 
 __global__ void __launch_bounds__(256) yidft_epi_kernel(
     const float2* __restrict__ Z, int n, int m, int Co, const float2* __restrict__ twY, float scale,
@@ -240,9 +241,9 @@ __global__ void __launch_bounds__(256) yidft_epi_kernel(
     extern __shared__ __align__(16) float sm[];
     float* twc = sm;                                            // [m][YT]  cos * c_ky * scale
     float* tws = twc + m * YT;                                  // [m][YT]  sin * c_ky * scale
-    float* xsT = tws + m * YT;                                  // [Ci][YT] (float4 reads: 16B aligned)
-    float2* Zs = reinterpret_cast<float2*>(xsT + Ci * YT);      // [m][Co]
-    float* Ws = xsT + Ci * YT + 2 * m * Co;                     // [Ci][Co]
+    float* xsT = tws + m * YT;                                  // [Ci][XP] (float4 reads: 16B aligned)
+    float2* Zs = reinterpret_cast<float2*>(xsT + Ci * XP);      // [m][Co]
+    float* Ws = xsT + Ci * XP + 2 * m * Co;                     // [Ci][Co]
     const long long R = blockIdx.x;
     for (int e = threadIdx.x; e < m * Co; e += blockDim.x) Zs[e] = Z[R * m * Co + e];
     for (int e = threadIdx.x; e < Ci * Co; e += blockDim.x) Ws[e] = Wm[e];
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(256) yidft_epi_kernel(
         }
         for (int e = threadIdx.x; e < YT * Ci; e += blockDim.x) {
             int yy = e / Ci, i = e % Ci;
-            xsT[i * YT + yy] = (yy < ny) ? x2[((R * n) + y0 + yy) * Ci + i] : 0.f;
+            xsT[i * XP + yy] = (yy < ny) ? x2[((R * n) + y0 + yy) * Ci + i] : 0.f;
         }
         __syncthreads();
         for (int w = threadIdx.x; w < (YT / 4) * Co; w += blockDim.x) {
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(256) yidft_epi_kernel(
             }
             for (int i = 0; i < Ci; ++i) {
                 const float wv = Ws[i * Co + o];
-                const float4 xv = *reinterpret_cast<const float4*>(xsT + i * YT + q * 4);
+                const float4 xv = *reinterpret_cast<const float4*>(xsT + i * XP + q * 4);
                 a0 = fmaf(xv.x, wv, a0);
                 a1 = fmaf(xv.y, wv, a1);
                 a2 = fmaf(xv.z, wv, a2);
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(256) yidft_epi_kernel(
 using namespace gb200;
 
 extern "C" int gb200_spectral_suggest_ysplit(long long R, int C, int n) {
-    long long ctas = (R * C + 255) / 256;
+    long long ctas = (R * C + 127) / 128;
     if (ctas >= 148 || n < 4 * YCH) return 1;
     int want = (int)((2 * 148 + ctas - 1) / ctas);
     int maxs = n / (2 * YCH);
@@ -330,10 +331,10 @@ extern "C" int gb200_spectral_ydft(int device, const float* x, long long R, int 
     const long long RC = R * C;
     int ychunk = cdiv(cdiv(n, nsplit), YCH) * YCH;
     nsplit = cdiv(n, ychunk);
-    dim3 grid(cdiv(RC, 256), nsplit, cdiv(m, KYG));
+    dim3 grid(cdiv(RC, 128), nsplit, cdiv(m, KYG));
     GB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gb200_spectral_ydft: grid too large");
     cudaStream_t st = as_stream(stream);
-    ydft_kernel<<<grid, 256, 0, st>>>(x, RC, C, n, m, reinterpret_cast<const float2*>(twY), scale, hermitian,
+    ydft_kernel<<<grid, 128, 0, st>>>(x, RC, C, n, m, reinterpret_cast<const float2*>(twY), scale, hermitian,
                                       nsplit, ychunk, reinterpret_cast<float2*>(out),
                                       reinterpret_cast<float2*>(workspace));
     if (nsplit > 1) {
@@ -415,7 +416,7 @@ extern "C" int gb200_spectral_yidft_epilogue(int device, const float* Z, long lo
     GB_REQUIRE(Z && twY && x2 && Wm && y, "gb200_spectral_yidft_epilogue: null argument");
     GB_REQUIRE(R >= 1 && R <= 0x7fffffffLL && n >= 1 && m >= 1 && Co >= 1 && Ci >= 1,
                "gb200_spectral_yidft_epilogue: bad shape");
-    size_t smem = (size_t)(2 * m * Co + Ci * Co + 2 * m * YT + Ci * YT) * sizeof(float);
+    size_t smem = (size_t)(2 * m * Co + Ci * Co + 2 * m * YT + Ci * XP) * sizeof(float);
     GB_REQUIRE(smem <= 200 * 1024, "gb200_spectral_yidft_epilogue: tile needs %zu B of shared memory", smem);
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(yidft_epi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -318,6 +318,7 @@ class _LinearAttentionFn(torch.autograd.Function):
         T, d = B * n, dk + p
         dev = _dev(query)
         st = stream_of(query)
+        tc = int(_PRECISION == "tf32")
         qkv = torch.empty((T, 3 * dm), dtype=torch.float32, device=query.device)
         xs = [t.reshape(T, dm) for t in (query, key, value)]
         if self_attn:      # one GEMM, N = 3*d_model
@@ -329,11 +330,10 @@ class _LinearAttentionFn(torch.autograd.Function):
         # which blocks are normalised: galerkin -> (K, V), fourier -> (Q, K)
         blocks = {"kv": (1, 2), "qk": (1, 0), None: ()}[norm_on]
         rstd = []
-        for blk in blocks:
-            r = torch.empty((T, H), dtype=torch.float32, device=query.device)
-            _launch("headnorm_fwd", 8.0 * T * dm, 8.0 * T * dm, lib.gb200_headnorm_fwd, dev, ptr(qkv), 3 * dm,
-                    blk * dm, T, H, dk, eps, ptr(r), st)
-            rstd.append(r)
+        if blocks:      # both normalised operand blocks in ONE launch
+            rstd = [torch.empty((T, H), dtype=torch.float32, device=query.device) for _ in blocks]
+            _launch("headnorm_fwd", 16.0 * T * dm, 16.0 * T * dm, lib.gb200_headnorm_fwd, dev, ptr(qkv), 3 * dm,
+                    blocks[0] * dm, blocks[1] * dm, T, H, dk, eps, ptr(rstd[0]), ptr(rstd[1]), st)
         aff = {0: (None, None), 1: (None, None), 2: (None, None)}
         if blocks:
             aff[blocks[0]] = (g1, b1)
@@ -346,10 +346,10 @@ class _LinearAttentionFn(torch.autograd.Function):
         xty_work = (2.0 * B * H * n * d * d, 4.0 * (2 * T * dm + T * p))
         xm_work = (2.0 * B * H * n * d * d, 4.0 * (T * dm + T * p + T * H * d))
         _launch("attn_xty", *xty_work, lib.gb200_attn_xty, dev, ops[1], ops[2], ptr(pos), B, H, n, dk, p, scale,
-                ptr(keep_mask), ptr(A), nsplit, ptr(ws), ws_bytes, st)
+                ptr(keep_mask), ptr(A), nsplit, ptr(ws), ws_bytes, tc, st)
         out = torch.empty((B, n, H * d), dtype=torch.float32, device=query.device)
         _launch("attn_xm", *xm_work, lib.gb200_attn_xm, dev, ops[0], ptr(pos), ptr(A), 0, B, H, n, dk, p,
-                ptr(out), H * d, 0, 1, 1.0, st)
+                ptr(out), H * d, 0, 1, 1.0, tc, st)
         ctx.save_for_backward(query, key, value, pos, wqkv, g1, b1, g2, b2, keep_mask, qkv, A, *rstd)
         ctx.cfg = cfg
         ctx.set_materialize_grads(False)
@@ -363,6 +363,7 @@ class _LinearAttentionFn(torch.autograd.Function):
         B, n, dm = query.shape
         T, d = B * n, dk + p
         dev, st = _dev(query), stream_of(query)
+        tc = int(_PRECISION == "tf32")
         dout = torch.zeros((B, n, H * d), dtype=torch.float32, device=query.device) if dout is None \
             else dout.contiguous()
         blocks = {"kv": (1, 2), "qk": (1, 0), None: ()}[norm_on]
@@ -381,10 +382,10 @@ class _LinearAttentionFn(torch.autograd.Function):
         ws = workspace(ws_bytes, qkv)
         if dA_ext is None:       # the usual case: nobody differentiates through the returned A
             _launch("attn_xty", *xty_work, lib.gb200_attn_xty, dev, ops[0], do_op, ptr(pos), B, H, n, dk, p,
-                    scale, ptr(keep_mask), ptr(G), nsplit, ptr(ws), ws_bytes, st)
+                    scale, ptr(keep_mask), ptr(G), nsplit, ptr(ws), ws_bytes, tc, st)
         else:
             _launch("attn_xty", *xty_work, lib.gb200_attn_xty, dev, ops[0], do_op, ptr(pos), B, H, n, dk, p, 1.0,
-                    None, ptr(G), nsplit, ptr(ws), ws_bytes, st)
+                    None, ptr(G), nsplit, ptr(ws), ws_bytes, tc, st)
             G = (G + dA_ext) * scale
             if keep_mask is not None:
                 G = G * (2.0 * keep_mask.to(G.dtype))
@@ -392,22 +393,20 @@ class _LinearAttentionFn(torch.autograd.Function):
         dqkv = torch.empty((T, 3 * dm), dtype=torch.float32, device=query.device)
         # dQ~ = dO A^T ; dV~ = K~ G ; dK~ = V~ G^T   (position columns carry no gradient)
         _launch("attn_xm", *xm_work, lib.gb200_attn_xm, dev, do_op, ptr(pos), ptr(A), 1, B, H, n, dk, p, ptr(dqkv),
-                3 * dm, 0, 0, 1.0, st)
+                3 * dm, 0, 0, 1.0, tc, st)
         _launch("attn_xm", *xm_work, lib.gb200_attn_xm, dev, ops[1], ptr(pos), ptr(G), 0, B, H, n, dk, p, ptr(dqkv),
-                3 * dm, 2 * dm, 0, 1.0, st)
+                3 * dm, 2 * dm, 0, 1.0, tc, st)
         _launch("attn_xm", *xm_work, lib.gb200_attn_xm, dev, ops[2], ptr(pos), ptr(G), 1, B, H, n, dk, p, ptr(dqkv),
-                3 * dm, dm, 0, 1.0, st)
+                3 * dm, dm, 0, 1.0, tc, st)
         dgb = [None, None, None, None]
-        for j, blk in enumerate(blocks):
-            gamma = (g1, g2)[j]
-            dg = torch.empty_like(gamma)
-            db = torch.empty_like(gamma)
+        if blocks:
+            dgb = [torch.empty_like(g1), torch.empty_like(g1), torch.empty_like(g2), torch.empty_like(g2)]
             wsb = lib.gb200_headnorm_bwd_workspace_bytes(T, H, dk)
             w2 = workspace(wsb, qkv)
-            _launch("headnorm_bwd", 14.0 * T * dm, 12.0 * T * dm, lib.gb200_headnorm_bwd, dev, ptr(dqkv), 3 * dm,
-                    blk * dm, ptr(qkv), 3 * dm, blk * dm, ptr(rstd[j]), ptr(gamma), T, H, dk, ptr(dg), ptr(db), 0,
+            _launch("headnorm_bwd", 28.0 * T * dm, 24.0 * T * dm, lib.gb200_headnorm_bwd, dev, ptr(dqkv), 3 * dm,
+                    blocks[0] * dm, blocks[1] * dm, ptr(qkv), 3 * dm, blocks[0] * dm, blocks[1] * dm, ptr(rstd[0]),
+                    ptr(rstd[1]), ptr(g1), ptr(g2), T, H, dk, ptr(dgb[0]), ptr(dgb[1]), ptr(dgb[2]), ptr(dgb[3]), 0,
                     ptr(w2), wsb, st)
-            dgb[2 * j], dgb[2 * j + 1] = dg, db
         # projection backward
         dwqkv = torch.empty_like(wqkv)
         dbqkv = torch.empty(3 * dm, dtype=torch.float32, device=query.device)

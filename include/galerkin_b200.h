@@ -110,31 +110,36 @@ typedef struct gb200_head_operand {
 } gb200_head_operand;
 
 /* per-head LayerNorm statistics: x[t, col0 + h*dk + :] <- (x - mean) * rstd in place; rstd (T,H).
- * libs/layers.py:846-851, 859-864 (the affine part is applied on load by the kernels below) */
-int gb200_headnorm_fwd(int device, float* x, int ld, int col0, long long T, int H, int dk, float eps,
-                       float* rstd, void* stream);
+ * A second operand block (col0b >= 0, rstd_b) is normalised by the same launch: Galerkin normalises K and V,
+ * Fourier Q and K.  libs/layers.py:846-851, 859-864 (the affine part is applied on load by the kernels below) */
+int gb200_headnorm_fwd(int device, float* x, int ld, int col0, int col0b, long long T, int H, int dk, float eps,
+                       float* rstd, float* rstd_b, void* stream);
 size_t gb200_headnorm_bwd_workspace_bytes(long long T, int H, int dk);
-/* dy (grad w.r.t. gamma*xhat+beta) is overwritten by the grad w.r.t. the un-normalised rows */
-int gb200_headnorm_bwd(int device, float* dy, int lddy, int dcol0, const float* xhat, int ldx, int xcol0,
-                       const float* rstd, const float* gamma, long long T, int H, int dk, float* dgamma,
-                       float* dbeta, int accumulate, float* workspace, size_t workspace_bytes,
-                       void* stream);
+/* dy (grad w.r.t. gamma*xhat+beta) is overwritten by the grad w.r.t. the un-normalised rows; *_b = second block
+ * (dcol0b < 0: absent) */
+int gb200_headnorm_bwd(int device, float* dy, int lddy, int dcol0, int dcol0b, const float* xhat, int ldx, int xcol0,
+                       int xcol0b, const float* rstd, const float* rstd_b, const float* gamma, const float* gamma_b,
+                       long long T, int H, int dk, float* dgamma, float* dbeta, float* dgamma_b, float* dbeta_b,
+                       int accumulate, float* workspace, size_t workspace_bytes, void* stream);
 
-/* out[b,h,i,j] = scale * (keep_mask ? 2*keep_mask : 1) * sum_t L~[b,t,h,i] * R~[b,t,h,j]
+/* tensor_cores != 0 (and d_k+p <= 64): operands rounded to TF32 (cvt.rna) and contracted with warp-level
+ * mma.sync.m16n8k8 (fp32 accumulate), tiles right-sized to d; 0: exact-fp32 SIMT FMAs.
+ * out[b,h,i,j] = scale * (keep_mask ? 2*keep_mask : 1) * sum_t L~[b,t,h,i] * R~[b,t,h,j]
  * forward: A = K~^T V~ / n with the reference's always-on p=0.5 dropout as an explicit keep-mask
  * (libs/layers.py:723, 728, 730-731); backward: dA = Q~^T dO. */
 int gb200_attn_suggest_nsplit(int B, int H, int n);
 size_t gb200_attn_xty_workspace_bytes(int B, int H, int d, int nsplit);
 int gb200_attn_xty(int device, const gb200_head_operand* L, const gb200_head_operand* R, const float* pos,
                    int B, int H, int n, int dk, int p, float scale, const unsigned char* keep_mask,
-                   float* out, int nsplit, float* workspace, size_t workspace_bytes, void* stream);
+                   float* out, int nsplit, float* workspace, size_t workspace_bytes, int tensor_cores,
+                   void* stream);
 
 /* out[b,t,h,:] = out_scale * L~[b,t,h,:] . (transM ? M[b,h]^T : M[b,h])
  * out_augmented: written head-merged as (T, H*(p+dk)) -- libs/layers.py:733, 892-894;
  * else the p position columns are dropped and (T, ldo) is written at ocol0 + h*dk (gradients). */
 int gb200_attn_xm(int device, const gb200_head_operand* L, const float* pos, const float* M, int transM,
                   int B, int H, int n, int dk, int p, float* out, int ldo, int ocol0, int out_augmented,
-                  float out_scale, void* stream);
+                  float out_scale, int tensor_cores, void* stream);
 
 /* ------------------------------------------------------------------ spectral convolution ----
  * Mode-truncated DFT pipeline replacing rfft/rfft2 -> mode slice -> complex einsum -> zero pad ->

@@ -176,10 +176,14 @@ def test_layernorm_fwd_bwd():
         assert rel_l2(a, r) < 1e-5
 
 
+@pytest.mark.parametrize("tc", [0, 1])
 @pytest.mark.parametrize("B,H,n,dk,p", [(2, 4, 49, 8, 2), (1, 1, 300, 48, 2), (3, 2, 1000, 16, 1),
-                                        (2, 1, 130, 96, 1), (2, 4, 77, 32, 0)])
-def test_attention_core_kernels(B, H, n, dk, p):
+                                        (2, 1, 130, 96, 1), (2, 4, 77, 32, 0), (8, 4, 1849, 32, 2),
+                                        (2, 2, 513, 62, 2), (1, 3, 200, 22, 1)])
+def test_attention_core_kernels(B, H, n, dk, p, tc):
+    """tc=0: exact-fp32 SIMT kernels; tc=1: warp-level TF32 mma.sync kernels (d <= 64)."""
     lib = _lib.load()
+    tol = TF32_TOL if tc else 5e-6
     dm, d, T = H * dk, dk + p, B * n
     qkv = rn(T, 3 * dm)
     pos = torch.rand(B, n, max(p, 1), device=DEV)[..., :p].contiguous() if p else None
@@ -202,35 +206,37 @@ def test_attention_core_kernels(B, H, n, dk, p):
     wsb = lib.gb200_attn_xty_workspace_bytes(B, H, d, nsplit)
     ws = _lib.workspace(wsb, qkv)
     _lib.check(lib.gb200_attn_xty(dev, ops[1], ops[2], _lib.ptr(pos), B, H, n, dk, p, 1.0 / n, _lib.ptr(mask),
-                                  _lib.ptr(A), nsplit, _lib.ptr(ws), wsb, st))
+                                  _lib.ptr(A), nsplit, _lib.ptr(ws), wsb, tc, st))
     Aref = (k.transpose(-1, -2) @ v) / n * (2.0 * mask.double())
-    assert rel_l2(A, Aref) < 5e-6
+    assert rel_l2(A, Aref) < tol
     out = torch.empty(B, n, H * d, device=DEV)
     _lib.check(lib.gb200_attn_xm(dev, ops[0], _lib.ptr(pos), _lib.ptr(A), 0, B, H, n, dk, p, _lib.ptr(out), H * d,
-                                 0, 1, 1.0, st))
+                                 0, 1, 1.0, tc, st))
     oref = (q @ A.double()).permute(0, 2, 1, 3).reshape(B, n, H * d)
-    assert rel_l2(out, oref) < 5e-6
+    assert rel_l2(out, oref) < tol
     # transposed multiply, non-augmented output (gradient layout)
     dq = torch.zeros(T, 3 * dm, device=DEV)
     do = GF._hop(out, H * d, 0, True)
     _lib.check(lib.gb200_attn_xm(dev, do, _lib.ptr(pos), _lib.ptr(A), 1, B, H, n, dk, p, _lib.ptr(dq), 3 * dm, dm,
-                                 0, 1.0, st))
+                                 0, 1.0, tc, st))
     ref = (oref.view(B, n, H, d).permute(0, 2, 1, 3) @ A.double().transpose(-1, -2))[..., p:]
     ref = ref.permute(0, 2, 1, 3).reshape(T, dm)
-    assert rel_l2(dq[:, dm:2 * dm], ref) < 5e-6
+    assert rel_l2(dq[:, dm:2 * dm], ref) < tol
     assert dq[:, :dm].abs().max() == 0 and dq[:, 2 * dm:].abs().max() == 0
 
 
-def test_headnorm_fwd_bwd():
+@pytest.mark.parametrize("T,H,dk", [(777, 4, 32), (500, 4, 12), (1000, 1, 96), (333, 2, 16)])
+def test_headnorm_fwd_bwd(T, H, dk):
+    """(4,32) and (2,16) take the coalesced float4/shuffle kernels, the others the generic ones."""
     lib = _lib.load()
-    T, H, dk, eps = 777, 4, 32, 1e-7
+    eps = 1e-7
     dm = H * dk
     raw = rn(T, 3 * dm)
     gam = 1 + 0.2 * rn(H, dk, seed=1)
     buf = raw.clone()
     rstd = torch.empty(T, H, device=DEV)
     st = torch.cuda.current_stream().cuda_stream
-    _lib.check(lib.gb200_headnorm_fwd(0, _lib.ptr(buf), 3 * dm, dm, T, H, dk, eps, _lib.ptr(rstd), st))
+    _lib.check(lib.gb200_headnorm_fwd(0, _lib.ptr(buf), 3 * dm, dm, -1, T, H, dk, eps, _lib.ptr(rstd), None, st))
     x = raw[:, dm:2 * dm].double().view(T, H, dk).requires_grad_(True)
     mu, var = x.mean(-1, keepdim=True), x.var(-1, unbiased=False, keepdim=True)
     xhat = (x - mu) / torch.sqrt(var + eps)
@@ -243,8 +249,9 @@ def test_headnorm_fwd_bwd():
     dg, db = torch.empty(H, dk, device=DEV), torch.empty(H, dk, device=DEV)
     wsb = lib.gb200_headnorm_bwd_workspace_bytes(T, H, dk)
     ws = _lib.workspace(wsb, buf)
-    _lib.check(lib.gb200_headnorm_bwd(0, _lib.ptr(dbuf), 3 * dm, dm, _lib.ptr(buf), 3 * dm, dm, _lib.ptr(rstd),
-                                      _lib.ptr(gam), T, H, dk, _lib.ptr(dg), _lib.ptr(db), 0, _lib.ptr(ws), wsb, st))
+    _lib.check(lib.gb200_headnorm_bwd(0, _lib.ptr(dbuf), 3 * dm, dm, -1, _lib.ptr(buf), 3 * dm, dm, -1, _lib.ptr(rstd),
+                                      None, _lib.ptr(gam), None, T, H, dk, _lib.ptr(dg), _lib.ptr(db), None, None, 0,
+                                      _lib.ptr(ws), wsb, st))
     assert rel_l2(dbuf[:, dm:2 * dm], gx.reshape(T, dm)) < 1e-5
     dyk = dy[:, dm:2 * dm].double().view(T, H, dk)
     assert rel_l2(dg, (dyk * xhat.detach()).sum(0)) < 1e-5 and rel_l2(db, dyk.sum(0)) < 1e-5
