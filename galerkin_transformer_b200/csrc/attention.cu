@@ -308,8 +308,10 @@ __global__ void __launch_bounds__(256) xty_kernel(HeadOperand L, HeadOperand R, 
 // A[bh][i][j] = scale * sum_s P[bh][s][i][j] * (mask ? 2*mask : 1); optionally also the
 // un-masked value (needed by nothing downstream; kept null) -- fixed summation order.
 __global__ void xty_reduce_kernel(const float* __restrict__ part, int nsplit, int dd, long long total,
-                                  float scale, const unsigned char* __restrict__ mask,
+                                  float scale, const unsigned char* __restrict__ mask, float mask_p,
+                                  unsigned long long mask_seed, const unsigned long long* seed_off,
                                   float* __restrict__ out) {
+    if (mask_p > 0.f && seed_off) mask_seed += *seed_off;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x) {
         long long bh = e / dd;
@@ -319,6 +321,7 @@ __global__ void xty_reduce_kernel(const float* __restrict__ part, int nsplit, in
         for (int k = 0; k < nsplit; ++k) s += p[(long long)k * dd];
         s *= scale;
         if (mask) s *= 2.f * (float)mask[e];
+        else if (mask_p > 0.f) s *= dropout_scale(mask_p, mask_seed, (unsigned long long)e);   // 0 or 1/(1-p)
         out[e] = s;
     }
 }
@@ -515,8 +518,9 @@ extern "C" size_t gb200_attn_xty_workspace_bytes(int B, int H, int d, int nsplit
 
 extern "C" int gb200_attn_xty(int device, const gb200_head_operand* L, const gb200_head_operand* R,
                               const float* pos, int B, int H, int n, int dk, int p, float scale,
-                              const unsigned char* keep_mask, float* out, int nsplit, float* workspace,
-                              size_t workspace_bytes, int tensor_cores, void* stream) {
+                              const unsigned char* keep_mask, float mask_p, unsigned long long mask_seed,
+                              float* out, int nsplit, float* workspace, size_t workspace_bytes, int tensor_cores,
+                              void* stream) {
     use_device(device);
     GB_REQUIRE(L && R && out && L->ptr && R->ptr, "gb200_attn_xty: null operand");
     GB_REQUIRE(B >= 1 && H >= 1 && n >= 1 && dk >= 1 && p >= 0, "gb200_attn_xty: bad shape");
@@ -543,8 +547,30 @@ extern "C" int gb200_attn_xty(int device, const gb200_head_operand* L, const gb2
     long long total = (long long)B * H * d * d;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    xty_reduce_kernel<<<blocks, 256, 0, st>>>(workspace, nsplit, d * d, total, scale, keep_mask, out);
+    GB_REQUIRE(mask_p >= 0.f && mask_p < 1.f, "gb200_attn_xty: mask_p=%f outside [0,1)", mask_p);
+    xty_reduce_kernel<<<blocks, 256, 0, st>>>(workspace, nsplit, d * d, total, scale, keep_mask, mask_p, mask_seed,
+                                              rng_offset_ptr(), out);
     return check_launch("gb200_attn_xty", 2);
+}
+
+// scale tensor of the in-kernel attention dropout: out[e] = 0 or 1/(1-p), same stream as gb200_attn_xty
+__global__ void philox_scale_kernel(float* __restrict__ out, long long total, float p, unsigned long long seed,
+                                    const unsigned long long* seed_off) {
+    if (seed_off) seed += *seed_off;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x)
+        out[e] = dropout_scale(p, seed, (unsigned long long)e);
+}
+
+extern "C" int gb200_philox_scale(int device, float* out, long long total, float p, unsigned long long seed,
+                                  void* stream) {
+    use_device(device);
+    GB_REQUIRE(out && total >= 0 && p >= 0.f && p < 1.f, "gb200_philox_scale: bad arguments");
+    if (total == 0) return GB200_OK;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    philox_scale_kernel<<<blocks, 256, 0, as_stream(stream)>>>(out, total, p, seed, rng_offset_ptr());
+    return check_launch("gb200_philox_scale");
 }
 
 extern "C" int gb200_attn_xm(int device, const gb200_head_operand* L, const float* pos, const float* M,

@@ -94,6 +94,14 @@ __device__ __forceinline__ void reduce_partials_2d(const float* __restrict__ par
     }
 }
 
+// four consecutive elements idx..idx+3 (idx % 4 == 0) from ONE Philox block -- same stream as dropout_scale
+__device__ __forceinline__ float4 dropout_scale4(float p, uint64_t seed, uint64_t idx) {
+    const uint4 r = philox4x32(seed, idx >> 2);
+    const float keep = 1.f / (1.f - p), k = 1.0f / 16777216.0f;
+    return make_float4((float)(r.x >> 8) * k < p ? 0.f : keep, (float)(r.y >> 8) * k < p ? 0.f : keep,
+                       (float)(r.z >> 8) * k < p ? 0.f : keep, (float)(r.w >> 8) * k < p ? 0.f : keep);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -198,9 +198,8 @@ __global__ void epilogue_bwd_vec4_kernel(const float4* __restrict__ dy, const fl
         float4 v = dy[e];
         v.x *= rscale; v.y *= rscale; v.z *= rscale; v.w *= rscale;
         if (drop_p > 0.f) {
-            const unsigned long long b = (unsigned long long)e * 4;
-            v.x *= dropout_scale(drop_p, seed, b);     v.y *= dropout_scale(drop_p, seed, b + 1);
-            v.z *= dropout_scale(drop_p, seed, b + 2); v.w *= dropout_scale(drop_p, seed, b + 3);
+            const float4 ds = dropout_scale4(drop_p, seed, (unsigned long long)e * 4);
+            v.x *= ds.x; v.y *= ds.y; v.z *= ds.z; v.w *= ds.w;
         }
         if (ACT == ACT_RELU) {
             const float4 r = ref[e];

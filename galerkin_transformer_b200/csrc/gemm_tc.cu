@@ -152,9 +152,8 @@ __device__ __forceinline__ void tc_epilogue_vec4(const TcArgs& g, const float* _
                 if (hasZ) *reinterpret_cast<float4*>(zp + (long long)(r0 + i) * ep.ldz) = z;
                 float4 v = make_float4(act_fast<ACT>(z.x), act_fast<ACT>(z.y), act_fast<ACT>(z.z), act_fast<ACT>(z.w));
                 if (DROP) {
-                    const unsigned long long e = (unsigned long long)(rbase + r0 + i) * g.N + n;
-                    v.x *= dropout_scale(p, seed, e);     v.y *= dropout_scale(p, seed, e + 1);
-                    v.z *= dropout_scale(p, seed, e + 2); v.w *= dropout_scale(p, seed, e + 3);
+                    const float4 ds = dropout_scale4(p, seed, (unsigned long long)(rbase + r0 + i) * g.N + n);
+                    v.x *= ds.x; v.y *= ds.y; v.z *= ds.z; v.w *= ds.w;
                 }
                 *reinterpret_cast<float4*>(cp + (long long)(r0 + i) * ep.ldc) =
                     make_float4(fmaf(rscale, v.x, rv[i].x), fmaf(rscale, v.y, rv[i].y), fmaf(rscale, v.z, rv[i].z),

@@ -207,7 +207,9 @@ def linear(x, weight, bias=None, *, act="none", residual=None, rscale=1.0, drop_
 
 class _LinearCatFn(torch.autograd.Function):
     """y = [x1 | x2] @ W^T + b without materialising the concatenation
-    (torch.cat([x, grid], -1) -> fc, libs/model.py:615-617)."""
+    (torch.cat([x, grid], -1) -> fc, libs/model.py:615-617).  The weight is split into two contiguous
+    blocks so the wide part (K1 = n_hidden) keeps TMA-legal pitches and runs on the tensor cores; the
+    2-column coordinate part is a K=2 SIMT update."""
 
     @staticmethod
     def forward(ctx, x1, x2, weight, bias):
@@ -216,31 +218,35 @@ class _LinearCatFn(torch.autograd.Function):
         K2 = x2.shape[1]
         N, K = weight.shape
         assert K == K1 + K2
+        w1 = weight[:, :K1].contiguous()
+        w2 = weight[:, K1:].contiguous()
         y = torch.empty((M, N), dtype=torch.float32, device=x1.device)
-        gemm(x1, weight, y, M, N, K1, lda=K1, ldb=K, ldc=N, transB=True, bias=bias)
-        gemm(x2, weight, y, M, N, K2, lda=K2, ldb=K, ldc=N, transB=True, accumulate=True, b_off=K1)
-        ctx.save_for_backward(x1, x2, weight)
+        gemm(x1, w1, y, M, N, K1, lda=K1, ldb=K1, ldc=N, transB=True, bias=bias)
+        gemm(x2, w2, y, M, N, K2, lda=K2, ldb=K2, ldc=N, transB=True, accumulate=True)
+        ctx.save_for_backward(x1, x2, w1, w2)
         ctx.has_bias = bias is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x1, x2, weight = ctx.saved_tensors
+        x1, x2, w1, w2 = ctx.saved_tensors
         dy = dy.contiguous()
         M, K1 = x1.shape
         K2 = x2.shape[1]
-        N, K = weight.shape
+        N = w1.shape[0]
         dx1 = dx2 = dw = db = None
         if ctx.needs_input_grad[0]:
             dx1 = torch.empty_like(x1)
-            gemm(dy, weight, dx1, M, K1, N, lda=N, ldb=K, ldc=K1)
+            gemm(dy, w1, dx1, M, K1, N, lda=N, ldb=K1, ldc=K1)
         if ctx.needs_input_grad[1]:
             dx2 = torch.empty_like(x2)
-            gemm(dy, weight, dx2, M, K2, N, lda=N, ldb=K, ldc=K2, b_off=K1)
+            gemm(dy, w2, dx2, M, K2, N, lda=N, ldb=K2, ldc=K2)
         if ctx.needs_input_grad[2]:
-            dw = torch.empty_like(weight)
-            gemm(dy, x1, dw, N, K1, M, lda=N, ldb=K1, ldc=K, transA=True)
-            gemm(dy, x2, dw, N, K2, M, lda=N, ldb=K2, ldc=K, transA=True, c_off=K1)
+            dw1 = torch.empty_like(w1)
+            dw2 = torch.empty_like(w2)
+            gemm(dy, x1, dw1, N, K1, M, lda=N, ldb=K1, ldc=K1, transA=True)
+            gemm(dy, x2, dw2, N, K2, M, lda=N, ldb=K2, ldc=K2, transA=True)
+            dw = torch.cat([dw1, dw2], dim=1)
         if ctx.has_bias and ctx.needs_input_grad[3]:
             db = torch.empty(N, dtype=torch.float32, device=dy.device)
             colsum(dy, M, N, N, db)
@@ -311,7 +317,7 @@ class _LinearAttentionFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, query, key, value, pos, wqkv, bqkv, g1, b1, g2, b2, keep_mask, cfg):
-        H, dk, p, eps, norm_on, scale, self_attn = cfg
+        H, dk, p, eps, norm_on, scale, self_attn, mask_p, mask_seed = cfg
         require_cuda_f32(query, key, value, pos, wqkv, bqkv, g1, b1, g2, b2)
         lib = _lib.load()
         B, n, dm = query.shape
@@ -346,7 +352,7 @@ class _LinearAttentionFn(torch.autograd.Function):
         xty_work = (2.0 * B * H * n * d * d, 4.0 * (2 * T * dm + T * p))
         xm_work = (2.0 * B * H * n * d * d, 4.0 * (T * dm + T * p + T * H * d))
         _launch("attn_xty", *xty_work, lib.gb200_attn_xty, dev, ops[1], ops[2], ptr(pos), B, H, n, dk, p, scale,
-                ptr(keep_mask), ptr(A), nsplit, ptr(ws), ws_bytes, tc, st)
+                ptr(keep_mask), mask_p, mask_seed, ptr(A), nsplit, ptr(ws), ws_bytes, tc, st)
         out = torch.empty((B, n, H * d), dtype=torch.float32, device=query.device)
         _launch("attn_xm", *xm_work, lib.gb200_attn_xm, dev, ops[0], ptr(pos), ptr(A), 0, B, H, n, dk, p,
                 ptr(out), H * d, 0, 1, 1.0, tc, st)
@@ -358,7 +364,7 @@ class _LinearAttentionFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout, dA_ext):
         (query, key, value, pos, wqkv, g1, b1, g2, b2, keep_mask, qkv, A, *rstd) = ctx.saved_tensors
-        H, dk, p, eps, norm_on, scale, self_attn = ctx.cfg
+        H, dk, p, eps, norm_on, scale, self_attn, mask_p, mask_seed = ctx.cfg
         lib = _lib.load()
         B, n, dm = query.shape
         T, d = B * n, dk + p
@@ -382,13 +388,17 @@ class _LinearAttentionFn(torch.autograd.Function):
         ws = workspace(ws_bytes, qkv)
         if dA_ext is None:       # the usual case: nobody differentiates through the returned A
             _launch("attn_xty", *xty_work, lib.gb200_attn_xty, dev, ops[0], do_op, ptr(pos), B, H, n, dk, p,
-                    scale, ptr(keep_mask), ptr(G), nsplit, ptr(ws), ws_bytes, tc, st)
+                    scale, ptr(keep_mask), mask_p, mask_seed, ptr(G), nsplit, ptr(ws), ws_bytes, tc, st)
         else:
             _launch("attn_xty", *xty_work, lib.gb200_attn_xty, dev, ops[0], do_op, ptr(pos), B, H, n, dk, p, 1.0,
-                    None, ptr(G), nsplit, ptr(ws), ws_bytes, tc, st)
+                    None, 0.0, 0, ptr(G), nsplit, ptr(ws), ws_bytes, tc, st)
             G = (G + dA_ext) * scale
             if keep_mask is not None:
                 G = G * (2.0 * keep_mask.to(G.dtype))
+            elif mask_p > 0.0:
+                drop = torch.empty_like(G)
+                check(lib.gb200_philox_scale(dev, ptr(drop), drop.numel(), mask_p, mask_seed, st), "gb200_philox_scale")
+                G = G * drop
             G = G.contiguous()
         dqkv = torch.empty((T, 3 * dm), dtype=torch.float32, device=query.device)
         # dQ~ = dO A^T ; dV~ = K~ G ; dK~ = V~ G^T   (position columns carry no gradient)
@@ -433,8 +443,9 @@ class _LinearAttentionFn(torch.autograd.Function):
 
 
 def linear_attention(query, key, value, pos, wqkv, bqkv, norm_params, keep_mask, *, n_head, pos_dim,
-                     eps, attention_type, self_attn):
-    """Returns (head-merged output (B, n, H*(d_k+p)), A (B,H,d,d))."""
+                     eps, attention_type, self_attn, mask_p=0.0):
+    """keep_mask: explicit (B,H,d,d) uint8 keep-mask, or None with mask_p > 0 for the in-kernel Philox
+    dropout of the attention matrix (no mask tensor, regenerated in backward)."""
     B, n, dm = query.shape
     dk = dm // n_head
     p = pos_dim if pos is not None else 0
@@ -446,7 +457,9 @@ def linear_attention(query, key, value, pos, wqkv, bqkv, norm_params, keep_mask,
     g1 = b1 = g2 = b2 = None
     if norm_params is not None:
         g1, b1, g2, b2 = norm_params
-    cfg = (n_head, dk, p, float(eps), norm_on, float(scale), bool(self_attn))
+    mask_p = 0.0 if keep_mask is not None else float(mask_p)
+    cfg = (n_head, dk, p, float(eps), norm_on, float(scale), bool(self_attn), mask_p,
+           next_seed() if mask_p > 0.0 else 0)
     pos_c = None if pos is None else pos.contiguous()
     return _LinearAttentionFn.apply(query.contiguous(), key.contiguous(), value.contiguous(), pos_c, wqkv, bqkv,
                                     g1, b1, g2, b2, keep_mask, cfg)

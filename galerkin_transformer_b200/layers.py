@@ -134,12 +134,13 @@ class SimpleAttention(nn.Module):
 
         keep = self._next_mask
         self._next_mask = None
+        mask_p = 0.0
         if keep is None and self.attn_dropout == 'reference':
             if self.attention_type in _FOURIER:
                 raise NotImplementedError(
                     "Fourier-type attention with the reference's n x n p=0.5 dropout needs the quadratic "
                     "kernel; set module.attn_dropout='off' to use the exact linear-form path")
-            keep = (torch.rand((bsz, self.n_head, d, d), device=query.device) >= 0.5).to(torch.uint8)
+            mask_p = 0.5          # drawn inside the K^T V reduction kernel (Philox), never materialised
         elif keep is not None:
             if self.attention_type in _FOURIER:
                 raise NotImplementedError("explicit n x n keep-masks for Fourier-type attention")
@@ -149,7 +150,7 @@ class SimpleAttention(nn.Module):
                                       self._norm_params(), keep, n_head=self.n_head, pos_dim=p,
                                       eps=self.eps, attention_type='galerkin'
                                       if self.attention_type in _GALERKIN else 'fourier',
-                                      self_attn=self_attn)
+                                      self_attn=self_attn, mask_p=mask_p)
         # Galerkin: the (B,H,d,d) matrix K^T V / n (post-dropout), as the reference returns.
         # Fourier: the reference keeps the (B,H,n,n) matrix alive; it is never materialised here.
         self.attn_weight = attn if self.attention_type in _GALERKIN else None

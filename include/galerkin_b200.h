@@ -124,15 +124,20 @@ int gb200_headnorm_bwd(int device, float* dy, int lddy, int dcol0, int dcol0b, c
 
 /* tensor_cores != 0 (and d_k+p <= 64): operands rounded to TF32 (cvt.rna) and contracted with warp-level
  * mma.sync.m16n8k8 (fp32 accumulate), tiles right-sized to d; 0: exact-fp32 SIMT FMAs.
- * out[b,h,i,j] = scale * (keep_mask ? 2*keep_mask : 1) * sum_t L~[b,t,h,i] * R~[b,t,h,j]
+ * out[b,h,i,j] = scale * drop[b,h,i,j] * sum_t L~[b,t,h,i] * R~[b,t,h,j], where drop is
+ *   2*keep_mask (explicit uint8 keep-mask), else the in-kernel Philox draw with keep-probability 1-mask_p scaled
+ *   by 1/(1-mask_p) (mask_p = 0.5 reproduces F.dropout(p_attn), libs/layers.py:730-731; the same mask_seed in
+ *   backward regenerates the same mask), else 1 (mask_p = 0).
  * forward: A = K~^T V~ / n with the reference's always-on p=0.5 dropout as an explicit keep-mask
  * (libs/layers.py:723, 728, 730-731); backward: dA = Q~^T dO. */
 int gb200_attn_suggest_nsplit(int B, int H, int n);
 size_t gb200_attn_xty_workspace_bytes(int B, int H, int d, int nsplit);
 int gb200_attn_xty(int device, const gb200_head_operand* L, const gb200_head_operand* R, const float* pos,
-                   int B, int H, int n, int dk, int p, float scale, const unsigned char* keep_mask,
-                   float* out, int nsplit, float* workspace, size_t workspace_bytes, int tensor_cores,
-                   void* stream);
+                   int B, int H, int n, int dk, int p, float scale, const unsigned char* keep_mask, float mask_p,
+                   unsigned long long mask_seed, float* out, int nsplit, float* workspace,
+                   size_t workspace_bytes, int tensor_cores, void* stream);
+/* out[e] = 0 or 1/(1-p): the scale tensor of the in-kernel dropout stream (seed, element index) */
+int gb200_philox_scale(int device, float* out, long long total, float p, unsigned long long seed, void* stream);
 
 /* out[b,t,h,:] = out_scale * L~[b,t,h,:] . (transM ? M[b,h]^T : M[b,h])
  * out_augmented: written head-merged as (T, H*(p+dk)) -- libs/layers.py:733, 892-894;

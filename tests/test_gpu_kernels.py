@@ -206,7 +206,7 @@ def test_attention_core_kernels(B, H, n, dk, p, tc):
     wsb = lib.gb200_attn_xty_workspace_bytes(B, H, d, nsplit)
     ws = _lib.workspace(wsb, qkv)
     _lib.check(lib.gb200_attn_xty(dev, ops[1], ops[2], _lib.ptr(pos), B, H, n, dk, p, 1.0 / n, _lib.ptr(mask),
-                                  _lib.ptr(A), nsplit, _lib.ptr(ws), wsb, tc, st))
+                                  0.0, 0, _lib.ptr(A), nsplit, _lib.ptr(ws), wsb, tc, st))
     Aref = (k.transpose(-1, -2) @ v) / n * (2.0 * mask.double())
     assert rel_l2(A, Aref) < tol
     out = torch.empty(B, n, H * d, device=DEV)
