@@ -63,10 +63,14 @@ SIGNATURES = {
     "gb200_philox_scale": (c_int, [c_int, c_vp, c_ll, c_float, c_ull, c_vp]),
     "gb200_attn_xm": (c_int, [c_int, _HOP, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp,
                               c_int, c_int, c_int, c_float, c_int, c_vp]),
+    "gb200_fourier_quad_fwd": (c_int, [c_int, _HOP, _HOP, _HOP, c_vp, c_int, c_int, c_int, c_int, c_int, c_float, c_vp,
+                                       c_float, c_ull, c_vp, c_vp, c_vp]),
+    "gb200_fourier_quad_bwd": (c_int, [c_int, _HOP, _HOP, _HOP, _HOP, c_vp, c_int, c_int, c_int, c_int, c_int, c_float,
+                                       c_vp, c_float, c_ull, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "gb200_spectral_suggest_ysplit": (c_int, [c_ll, c_int, c_int]),
     "gb200_spectral_ydft_workspace_bytes": (c_sz, [c_ll, c_int, c_int, c_int]),
     "gb200_spectral_ydft": (c_int, [c_int, c_vp, c_ll, c_int, c_int, c_int, c_vp, c_float, c_int, c_vp,
-                                    c_int, c_vp, c_sz, c_vp]),
+                                    c_int, c_vp, c_sz, c_int, c_vp]),
     "gb200_spectral_xdft": (c_int, [c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_float, c_int, c_vp,
                                     c_vp]),
     "gb200_spectral_mix_fwd": (c_int, [c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp,
@@ -74,7 +78,7 @@ SIGNATURES = {
     "gb200_spectral_mix_bwd": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
                                        c_vp, c_vp, c_vp, c_int, c_vp]),
     "gb200_spectral_yidft_epilogue": (c_int, [c_int, c_vp, c_ll, c_int, c_int, c_int, c_vp, c_float, c_int,
-                                              c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
+                                              c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp]),
 }
 
 

@@ -7,14 +7,9 @@
 // staging tokens into shared memory, rounded to TF32 with cvt.rna.
 #pragma once
 #include "common.cuh"
+#include "mma_tf32.cuh"
 
 namespace gb200 {
-
-__device__ __forceinline__ float to_tf32(float v) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return __uint_as_float(r);
-}
 
 // Stage TT token rows of one head's augmented operand into shared memory S[r][i] (pitch P floats), features
 // i < DPAD (zero beyond d and beyond the last token), rounded to TF32.  Lane = feature column, so the column
@@ -64,18 +59,9 @@ __device__ __forceinline__ void stage_aug(float* __restrict__ S, const HeadOpera
     }
 }
 
-// D(16x8) += A(16x8, row) * B(8x8, col), TF32 inputs, fp32 accumulate
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], const float (&b)[2]) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-        : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])),
-          "r"(__float_as_uint(a[3])), "r"(__float_as_uint(b[0])), "r"(__float_as_uint(b[1])));
-}
-
 // ---- xty: P[i][j] = sum_t L~[t][i] R~[t][j];  MT x NT tiles of 16 x 8, i < 16*MT, j < 8*NT --------------
 template <int MT, int NT>
-__global__ void __launch_bounds__(256, 2) xty_mma_kernel(HeadOperand L, HeadOperand R, const float* __restrict__ pos,
+__global__ void __launch_bounds__(256, (MT * NT <= 15) ? 2 : 1) xty_mma_kernel(HeadOperand L, HeadOperand R, const float* __restrict__ pos,
                                                       int p, int dk, int H, int n, int nsplit, int chunk,
                                                       float* __restrict__ part) {
     constexpr int TC = 64;                         // tokens per stage: 8 warps x 8 tokens (one k-step each)

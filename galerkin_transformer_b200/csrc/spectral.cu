@@ -19,6 +19,7 @@
 // backward pass is the same five kernels with the adjoint scalings (see functional.py), which
 // reproduces autograd-through-rfft2/irfft2 to round-off (checked in tests against the oracle).
 #include "common.cuh"
+#include "spectral_mma.cuh"
 
 namespace gb200 {
 
@@ -320,7 +321,7 @@ extern "C" size_t gb200_spectral_ydft_workspace_bytes(long long R, int C, int m,
 
 extern "C" int gb200_spectral_ydft(int device, const float* x, long long R, int n, int C, int m,
                                    const float* twY, float scale, int hermitian, float* out, int nsplit,
-                                   float* workspace, size_t workspace_bytes, void* stream) {
+                                   float* workspace, size_t workspace_bytes, int tensor_cores, void* stream) {
     use_device(device);
     GB_REQUIRE(x && twY && out && R >= 1 && n >= 1 && C >= 1 && m >= 1, "gb200_spectral_ydft: bad arguments");
     GB_REQUIRE(m <= n / 2 + 1, "gb200_spectral_ydft: modes=%d exceeds n/2+1 for n=%d", m, n);
@@ -328,12 +329,30 @@ extern "C" int gb200_spectral_ydft(int device, const float* x, long long R, int 
     if (nsplit > 1)
         GB_REQUIRE(workspace && workspace_bytes >= gb200_spectral_ydft_workspace_bytes(R, C, m, nsplit),
                    "gb200_spectral_ydft: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    if (tensor_cores && 2 * m <= 32 && C % 8 == 0 && C <= 64 && R >= 128 && n <= 1024) {
+        // per-row twiddle GEMM on warp-level TF32 MMA (2-D grids: many rows, short transform length)
+        const int KP = (n + 7) / 8 * 8;
+        const int AP = KP + ((4 - KP % 32 + 32) % 32);
+        const size_t smem = (size_t)32 * AP * sizeof(float);
+        dim3 grid(cdiv(R, SM_WARPS));
+#define YD(NT)                                                                                                 \
+    do {                                                                                                       \
+        if (smem > 48 * 1024)                                                                                  \
+            cudaFuncSetAttribute(ydft_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        ydft_mma_kernel<NT><<<grid, SM_WARPS * 32, smem, st>>>(x, R, n, C, m, reinterpret_cast<const float2*>(twY), \
+                                                              scale, hermitian, reinterpret_cast<float2*>(out)); \
+    } while (0)
+        switch (C / 8) { case 1: YD(1); break; case 2: YD(2); break; case 3: YD(3); break; case 4: YD(4); break;
+                         case 5: YD(5); break; case 6: YD(6); break; case 7: YD(7); break; default: YD(8); }
+#undef YD
+        return check_launch("gb200_spectral_ydft");
+    }
     const long long RC = R * C;
     int ychunk = cdiv(cdiv(n, nsplit), YCH) * YCH;
     nsplit = cdiv(n, ychunk);
     dim3 grid(cdiv(RC, 128), nsplit, cdiv(m, KYG));
     GB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gb200_spectral_ydft: grid too large");
-    cudaStream_t st = as_stream(stream);
     ydft_kernel<<<grid, 128, 0, st>>>(x, RC, C, n, m, reinterpret_cast<const float2*>(twY), scale, hermitian,
                                       nsplit, ychunk, reinterpret_cast<float2*>(out),
                                       reinterpret_cast<float2*>(workspace));
@@ -411,11 +430,39 @@ extern "C" int gb200_spectral_mix_bwd(int device, const float* Xf, const float* 
 extern "C" int gb200_spectral_yidft_epilogue(int device, const float* Z, long long R, int n, int m, int Co,
                                              const float* twY, float scale, int hermitian, const float* x2,
                                              int Ci, const float* Wm, const float* bias, int act, float* y,
-                                             float* zout, void* stream) {
+                                             float* zout, int tensor_cores, void* stream) {
     use_device(device);
     GB_REQUIRE(Z && twY && x2 && Wm && y, "gb200_spectral_yidft_epilogue: null argument");
     GB_REQUIRE(R >= 1 && R <= 0x7fffffffLL && n >= 1 && m >= 1 && Co >= 1 && Ci >= 1,
                "gb200_spectral_yidft_epilogue: bad shape");
+    if (tensor_cores && 2 * m <= 32 && Co <= 64 && Ci <= 64 && n <= 16384) {
+        const int KS = (2 * m + 7) / 8 * 8, MP = (n + 15) / 16 * 16;
+        const int SP = KS + ((4 - KS % 32 + 32) % 32);
+        const size_t smem2 = (size_t)MP * SP * sizeof(float);
+        if (smem2 <= 200 * 1024) {
+            const int mtiles = MP / 16;
+            int tiles_per_warp = mtiles;               // one warp per row unless rows alone cannot fill the GPU
+            while (tiles_per_warp > 4 && R * cdiv(mtiles, tiles_per_warp) < 8 * 148 * SM_WARPS)
+                tiles_per_warp = (tiles_per_warp + 1) / 2;
+            const int chunks = cdiv(mtiles, tiles_per_warp);
+            const long long warps = R * chunks;
+            dim3 grid((unsigned)cdiv(warps, SM_WARPS));
+            const int nt = (Co + 7) / 8;
+            cudaStream_t st2 = as_stream(stream);
+#define YI(NT)                                                                                                   \
+    do {                                                                                                         \
+        if (smem2 > 48 * 1024)                                                                                   \
+            cudaFuncSetAttribute(yidft_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2); \
+        yidft_mma_kernel<NT><<<grid, SM_WARPS * 32, smem2, st2>>>(                                               \
+            reinterpret_cast<const float2*>(Z), R, n, m, Co, reinterpret_cast<const float2*>(twY), scale, hermitian, \
+            x2, Ci, Wm, bias, act, y, zout, tiles_per_warp, chunks);                                             \
+    } while (0)
+            switch (nt) { case 1: YI(1); break; case 2: YI(2); break; case 3: YI(3); break; case 4: YI(4); break;
+                          case 5: YI(5); break; case 6: YI(6); break; case 7: YI(7); break; default: YI(8); }
+#undef YI
+            return check_launch("gb200_spectral_yidft_epilogue");
+        }
+    }
     size_t smem = (size_t)(2 * m * Co + Ci * Co + 2 * m * YT + Ci * XP) * sizeof(float);
     GB_REQUIRE(smem <= 200 * 1024, "gb200_spectral_yidft_epilogue: tile needs %zu B of shared memory", smem);
     if (smem > 48 * 1024)

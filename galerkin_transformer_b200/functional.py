@@ -317,7 +317,7 @@ class _LinearAttentionFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, query, key, value, pos, wqkv, bqkv, g1, b1, g2, b2, keep_mask, cfg):
-        H, dk, p, eps, norm_on, scale, self_attn, mask_p, mask_seed = cfg
+        H, dk, p, eps, norm_on, scale, self_attn, mask_p, mask_seed, quadratic, want_attn = cfg
         require_cuda_f32(query, key, value, pos, wqkv, bqkv, g1, b1, g2, b2)
         lib = _lib.load()
         B, n, dm = query.shape
@@ -345,6 +345,18 @@ class _LinearAttentionFn(torch.autograd.Function):
             aff[blocks[0]] = (g1, b1)
             aff[blocks[1]] = (g2, b2)
         ops = [_hop(qkv, 3 * dm, i * dm, False, *aff[i]) for i in range(3)]
+        if quadratic:
+            # (Q~ K~^T) V~ with an n x n dropout in between: flash-style quadratic kernels
+            out = torch.empty((B, n, H * d), dtype=torch.float32, device=query.device)
+            A = torch.empty((B, H, n, n) if want_attn else (0,), dtype=torch.float32, device=query.device)
+            _launch("fourier_quad_fwd", 4.0 * B * H * n * n * d, 4.0 * (3 * T * dm + T * H * d),
+                    lib.gb200_fourier_quad_fwd, dev, ops[0], ops[1], ops[2], ptr(pos), B, H, n, dk, p, scale,
+                    ptr(keep_mask), mask_p, mask_seed, ptr(out), ptr(A) if want_attn else None, st)
+            ctx.save_for_backward(query, key, value, pos, wqkv, g1, b1, g2, b2, keep_mask, qkv, A, *rstd)
+            ctx.cfg = cfg
+            ctx.set_materialize_grads(False)
+            ctx.mark_non_differentiable(A)
+            return out, A
         A = torch.empty((B, H, d, d), dtype=torch.float32, device=query.device)
         nsplit = lib.gb200_attn_suggest_nsplit(B, H, n)
         ws_bytes = lib.gb200_attn_xty_workspace_bytes(B, H, d, nsplit)
@@ -364,7 +376,7 @@ class _LinearAttentionFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout, dA_ext):
         (query, key, value, pos, wqkv, g1, b1, g2, b2, keep_mask, qkv, A, *rstd) = ctx.saved_tensors
-        H, dk, p, eps, norm_on, scale, self_attn, mask_p, mask_seed = ctx.cfg
+        H, dk, p, eps, norm_on, scale, self_attn, mask_p, mask_seed, quadratic, want_attn = ctx.cfg
         lib = _lib.load()
         B, n, dm = query.shape
         T, d = B * n, dk + p
@@ -379,6 +391,13 @@ class _LinearAttentionFn(torch.autograd.Function):
             aff[blocks[1]] = (g2, b2)
         ops = [_hop(qkv, 3 * dm, i * dm, False, *aff[i]) for i in range(3)]
         do_op = _hop(dout, H * d, 0, True)
+        if quadratic:
+            dqkv = torch.empty((T, 3 * dm), dtype=torch.float32, device=query.device)
+            _launch("fourier_quad_bwd", 10.0 * B * H * n * n * d, 4.0 * (6 * T * dm + T * H * d),
+                    lib.gb200_fourier_quad_bwd, dev, ops[0], ops[1], ops[2], do_op, ptr(pos), B, H, n, dk, p, scale,
+                    ptr(keep_mask), mask_p, mask_seed, ptr(dqkv), 3 * dm, 0, dm, 2 * dm, st)
+            return _LinearAttentionFn._finish_backward(ctx, dqkv, blocks, rstd, qkv, g1, g2, query, key, value, wqkv,
+                                                       H, dk, T, dm, self_attn, dev, st)
         # G = scale * mask2 * (Q~^T dO [+ external grad of A])
         G = torch.empty((B, H, d, d), dtype=torch.float32, device=query.device)
         xty_work = (2.0 * B * H * n * d * d, 4.0 * (T * dm + T * p + T * H * d))
@@ -408,6 +427,14 @@ class _LinearAttentionFn(torch.autograd.Function):
                 3 * dm, 2 * dm, 0, 1.0, tc, st)
         _launch("attn_xm", *xm_work, lib.gb200_attn_xm, dev, ops[2], ptr(pos), ptr(G), 1, B, H, n, dk, p, ptr(dqkv),
                 3 * dm, dm, 0, 1.0, tc, st)
+        return _LinearAttentionFn._finish_backward(ctx, dqkv, blocks, rstd, qkv, g1, g2, query, key, value, wqkv, H, dk,
+                                                   T, dm, self_attn, dev, st)
+
+    @staticmethod
+    def _finish_backward(ctx, dqkv, blocks, rstd, qkv, g1, g2, query, key, value, wqkv, H, dk, T, dm, self_attn, dev,
+                         st):
+        """per-head LayerNorm backward on the normalised blocks, then the Q/K/V projection backward"""
+        lib = _lib.load()
         dgb = [None, None, None, None]
         if blocks:
             dgb = [torch.empty_like(g1), torch.empty_like(g1), torch.empty_like(g2), torch.empty_like(g2)]
@@ -443,7 +470,7 @@ class _LinearAttentionFn(torch.autograd.Function):
 
 
 def linear_attention(query, key, value, pos, wqkv, bqkv, norm_params, keep_mask, *, n_head, pos_dim,
-                     eps, attention_type, self_attn, mask_p=0.0):
+                     eps, attention_type, self_attn, mask_p=0.0, quadratic=False, want_attn=False):
     """keep_mask: explicit (B,H,d,d) uint8 keep-mask, or None with mask_p > 0 for the in-kernel Philox
     dropout of the attention matrix (no mask tensor, regenerated in backward)."""
     B, n, dm = query.shape
@@ -459,7 +486,7 @@ def linear_attention(query, key, value, pos, wqkv, bqkv, norm_params, keep_mask,
         g1, b1, g2, b2 = norm_params
     mask_p = 0.0 if keep_mask is not None else float(mask_p)
     cfg = (n_head, dk, p, float(eps), norm_on, float(scale), bool(self_attn), mask_p,
-           next_seed() if mask_p > 0.0 else 0)
+           next_seed() if mask_p > 0.0 else 0, bool(quadratic), bool(want_attn))
     pos_c = None if pos is None else pos.contiguous()
     return _LinearAttentionFn.apply(query.contiguous(), key.contiguous(), value.contiguous(), pos_c, wqkv, bqkv,
                                     g1, b1, g2, b2, keep_mask, cfg)
@@ -499,7 +526,7 @@ def _ydft(x, R, n, C, m, twY, scale, hermitian):
     ws = workspace(ws_bytes, x)
     _launch("spectral_ydft", 4.0 * R * n * C * m, 4.0 * R * n * C + 8.0 * R * m * C, lib.gb200_spectral_ydft,
             _dev(x), ptr(x), R, n, C, m, ptr(twY), scale, int(hermitian), ptr(out), nsplit, ptr(ws), ws_bytes,
-            stream_of(x))
+            int(_PRECISION == "tf32"), stream_of(x))
     return out
 
 
@@ -519,7 +546,7 @@ def _yidft_epi(Z, R, n, m, Co, twY, scale, hermitian, x2, Ci, Wm, bias, act, wan
     _launch("spectral_yidft_epilogue", R * n * Co * (4.0 * m + 2.0 * Ci),
             4.0 * R * n * (Ci + Co * (1 + want_z)) + 8.0 * R * m * Co + 4.0 * Ci * Co,
             lib.gb200_spectral_yidft_epilogue, _dev(Z), ptr(Z), R, n, m, Co, ptr(twY), scale, int(hermitian),
-            ptr(x2), Ci, ptr(Wm), ptr(bias), act, ptr(y), ptr(z), stream_of(Z))
+            ptr(x2), Ci, ptr(Wm), ptr(bias), act, ptr(y), ptr(z), int(_PRECISION == "tf32"), stream_of(Z))
     return y, z
 
 

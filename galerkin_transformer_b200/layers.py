@@ -80,6 +80,7 @@ class SimpleAttention(nn.Module):
         self.dropout = nn.Dropout(dropout)
         self.debug = debug
         self.attn_dropout = 'reference'
+        self.materialize_attn = False
         self._next_mask = None
 
     def _reset_parameters(self):
@@ -135,25 +136,26 @@ class SimpleAttention(nn.Module):
         keep = self._next_mask
         self._next_mask = None
         mask_p = 0.0
+        fourier = self.attention_type in _FOURIER
         if keep is None and self.attn_dropout == 'reference':
-            if self.attention_type in _FOURIER:
-                raise NotImplementedError(
-                    "Fourier-type attention with the reference's n x n p=0.5 dropout needs the quadratic "
-                    "kernel; set module.attn_dropout='off' to use the exact linear-form path")
-            mask_p = 0.5          # drawn inside the K^T V reduction kernel (Philox), never materialised
+            mask_p = 0.5          # drawn inside the kernels (Philox), never materialised
         elif keep is not None:
-            if self.attention_type in _FOURIER:
-                raise NotImplementedError("explicit n x n keep-masks for Fourier-type attention")
+            want = (bsz, self.n_head, n, n) if fourier else (bsz, self.n_head, d, d)
+            assert tuple(keep.shape) == want, f"keep-mask shape {tuple(keep.shape)} != {want}"
             keep = keep.to(device=query.device, dtype=torch.uint8).contiguous()
+        # Fourier type: without a dropout between the two products (QK^T)V = Q(K^T V) exactly, so the O(n d^2)
+        # linear-form kernels are used; with the n x n dropout the quadratic flash-style kernels run instead.
+        quadratic = fourier and (keep is not None or mask_p > 0.0 or self.materialize_attn)
 
         x, attn = GF.linear_attention(query, key, value, pos if use_pos else None, wqkv, bqkv,
                                       self._norm_params(), keep, n_head=self.n_head, pos_dim=p,
-                                      eps=self.eps, attention_type='galerkin'
-                                      if self.attention_type in _GALERKIN else 'fourier',
-                                      self_attn=self_attn, mask_p=mask_p)
+                                      eps=self.eps, attention_type='fourier' if fourier else 'galerkin',
+                                      self_attn=self_attn, mask_p=mask_p, quadratic=quadratic,
+                                      want_attn=self.materialize_attn)
         # Galerkin: the (B,H,d,d) matrix K^T V / n (post-dropout), as the reference returns.
-        # Fourier: the reference keeps the (B,H,n,n) matrix alive; it is never materialised here.
-        self.attn_weight = attn if self.attention_type in _GALERKIN else None
+        # Fourier: the reference keeps the (B,H,n,n) matrix alive on the module; here it only exists when
+        # `materialize_attn` is set (SimpleTransformerEncoderLayer(attn_weight=True) sets it).
+        self.attn_weight = attn if (not fourier or self.materialize_attn) else None
         return x, self.attn_weight
 
 

@@ -76,6 +76,7 @@ class SimpleTransformerEncoderLayer(nn.Module):
         self.add_pos_emb = pos_emb
         self.debug = debug
         self.attn_weight = attn_weight
+        self.attn.materialize_attn = bool(attn_weight)
         self.__name__ = attention_type.capitalize() + 'TransformerEncoderLayer'
 
     def forward(self, x, pos=None, weight=None):

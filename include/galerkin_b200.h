@@ -146,16 +146,34 @@ int gb200_attn_xm(int device, const gb200_head_operand* L, const float* pos, con
                   int B, int H, int n, int dk, int p, float* out, int ldo, int ocol0, int out_augmented,
                   float out_scale, int tensor_cores, void* stream);
 
+/* Quadratic-form Fourier-type attention, out = drop(Q~ K~^T * scale) V~ with scale = 1/(sqrt(d) n), flash-style
+ * (the (B,H,n,n) matrix is only written if attn_or_null is given).  Used when an n x n dropout sits between the
+ * products: explicit uint8 keep-mask (B,H,n,n) or the in-kernel Philox draw (mask_p, mask_seed), which reproduces
+ * F.dropout(p_attn) of libs/layers.py:698-703; backward regenerates the same mask.  d_k + p <= 64.
+ * fwd: out (T, H*(p+dk)) head-merged;  bwd: dqkv (T, ld) receives dQ~, dK~, dV~ (position columns dropped) at the
+ * given column offsets, given dO in the head-merged layout. */
+int gb200_fourier_quad_fwd(int device, const gb200_head_operand* q, const gb200_head_operand* k,
+                           const gb200_head_operand* v, const float* pos, int B, int H, int n, int dk, int p,
+                           float scale, const unsigned char* keep_mask, float mask_p, unsigned long long mask_seed,
+                           float* out, float* attn_or_null, void* stream);
+int gb200_fourier_quad_bwd(int device, const gb200_head_operand* q, const gb200_head_operand* k,
+                           const gb200_head_operand* v, const gb200_head_operand* dO, const float* pos, int B, int H,
+                           int n, int dk, int p, float scale, const unsigned char* keep_mask, float mask_p,
+                           unsigned long long mask_seed, float* dqkv, int ld, int qcol0, int kcol0, int vcol0,
+                           void* stream);
+
 /* ------------------------------------------------------------------ spectral convolution ----
  * Mode-truncated DFT pipeline replacing rfft/rfft2 -> mode slice -> complex einsum -> zero pad ->
  * irfft/irfft2 (libs/layers.py:1086-1101, 1175-1189).  Complex buffers are interleaved (re,im).
- * twY: (m, n, 2) = (cos, sin)(2 pi ky Y / n);  twX: (2m, n, 2) for kx(r) = r (r<m) | n-2m+r. */
+ * twY: (m, n, 2) = (cos, sin)(2 pi ky Y / n);  twX: (2m, n, 2) for kx(r) = r (r<m) | n-2m+r.
+ * tensor_cores != 0: the two grid-sized stages (ydft, yidft_epilogue) run as per-row TF32 products against the
+ * twiddle matrix on warp-level mma.sync (operands rounded with cvt.rna, fp32 accumulate); 0: exact fp32 FMAs. */
 int gb200_spectral_suggest_ysplit(long long R, int C, int n);
 size_t gb200_spectral_ydft_workspace_bytes(long long R, int C, int m, int nsplit);
 /* out[R,ky,c] = scale * (hermitian ? c_ky : 1) * sum_Y x[R,Y,c] e^{-i 2pi ky Y/n} */
 int gb200_spectral_ydft(int device, const float* x, long long R, int n, int C, int m, const float* twY,
                         float scale, int hermitian, float* out, int nsplit, float* workspace,
-                        size_t workspace_bytes, void* stream);
+                        size_t workspace_bytes, int tensor_cores, void* stream);
 /* inverse == 0: out[b,r,ky,c] = scale * sum_X in[b,X,ky,c] e^{-i 2pi kx(r) X/n}
  * inverse == 1: out[b,X,ky,c] = scale * sum_r in[b,r,ky,c] e^{+i 2pi kx(r) X/n} */
 int gb200_spectral_xdft(int device, const float* in, int B, int n, int m, int C, const float* twX,
@@ -175,7 +193,7 @@ int gb200_spectral_mix_bwd(int device, const float* Xf, const float* dO, const f
 int gb200_spectral_yidft_epilogue(int device, const float* Z, long long R, int n, int m, int Co,
                                   const float* twY, float scale, int hermitian, const float* x2, int Ci,
                                   const float* Wm, const float* bias, int act, float* y, float* zout,
-                                  void* stream);
+                                  int tensor_cores, void* stream);
 
 #ifdef __cplusplus
 }
