@@ -48,6 +48,9 @@ SIGNATURES = {
     "gb200_colsum": (c_int, [c_int, c_vp, c_int, c_ll, c_int, c_float, c_int, c_vp, c_vp, c_sz, c_vp]),
     "gb200_epilogue_bwd": (c_int, [c_int, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_ll, c_int,
                                    c_int, c_float, c_float, c_ull, c_vp]),
+    "gb200_epilogue_bwd_bias_workspace_bytes": (c_sz, [c_ll, c_int]),
+    "gb200_epilogue_bwd_bias": (c_int, [c_int, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_ll, c_int,
+                                        c_int, c_float, c_float, c_ull, c_vp, c_vp, c_sz, c_vp]),
     "gb200_layernorm_fwd": (c_int, [c_int, c_vp, c_ll, c_int, c_vp, c_vp, c_float, c_vp, c_vp, c_vp, c_vp]),
     "gb200_layernorm_bwd_workspace_bytes": (c_sz, [c_ll, c_int]),
     "gb200_layernorm_bwd": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_vp, c_vp, c_vp,

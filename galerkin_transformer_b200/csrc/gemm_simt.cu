@@ -214,6 +214,52 @@ __global__ void epilogue_bwd_vec4_kernel(const float4* __restrict__ dy, const fl
     }
 }
 
+// epilogue backward fused with the bias gradient: thread = fixed column quad, rows strided, so the column sums of
+// g accumulate in registers while g is written; per-CTA partials are finished by colsum_final_kernel.
+constexpr int EB_BLOCKS = 296;
+template <int ACT>
+__global__ void __launch_bounds__(256) epilogue_bwd_bias_kernel(const float4* __restrict__ dy,
+                                                                const float4* __restrict__ ref,
+                                                                float4* __restrict__ gout, int M, int N, float rscale,
+                                                                float drop_p, unsigned long long seed,
+                                                                const unsigned long long* seed_off,
+                                                                float* __restrict__ part) {
+    __shared__ float4 red[256];
+    if (drop_p > 0.f && seed_off) seed += *seed_off;
+    const int rowq = N / 4, q = threadIdx.x % rowq, rsub = threadIdx.x / rowq, rpb = 256 / rowq;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = blockIdx.x * rpb + rsub; r < M; r += gridDim.x * rpb) {
+        const long long e = (long long)r * rowq + q;
+        float4 v = dy[e];
+        v.x *= rscale; v.y *= rscale; v.z *= rscale; v.w *= rscale;
+        if (drop_p > 0.f) {
+            const float4 ds = dropout_scale4(drop_p, seed, (unsigned long long)e * 4);
+            v.x *= ds.x; v.y *= ds.y; v.z *= ds.z; v.w *= ds.w;
+        }
+        if (ACT == ACT_RELU) {
+            const float4 rr = ref[e];
+            v.x = rr.x > 0.f ? v.x : 0.f; v.y = rr.y > 0.f ? v.y : 0.f;
+            v.z = rr.z > 0.f ? v.z : 0.f; v.w = rr.w > 0.f ? v.w : 0.f;
+        } else if (ACT == ACT_SILU) {
+            const float4 rr = ref[e];
+            v.x *= act_grad(ACT_SILU, rr.x); v.y *= act_grad(ACT_SILU, rr.y);
+            v.z *= act_grad(ACT_SILU, rr.z); v.w *= act_grad(ACT_SILU, rr.w);
+        }
+        gout[e] = v;
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < rowq) {
+        float4 t = red[threadIdx.x];
+        for (int k = 1; k < rpb; ++k) {
+            const float4 o = red[threadIdx.x + k * rowq];
+            t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+        }
+        reinterpret_cast<float4*>(part + (long long)blockIdx.x * N)[threadIdx.x] = t;
+    }
+}
+
 }  // namespace gb200
 
 using namespace gb200;
@@ -334,4 +380,52 @@ extern "C" int gb200_epilogue_bwd(int device, const float* dy, int lddy, const f
     epilogue_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(dy, lddy, z, ldz, y, ldy, g, ldg, M, N, act,
                                                                rscale, drop_p, seed, rng_offset_ptr());
     return check_launch("gb200_epilogue_bwd");
+}
+
+extern "C" size_t gb200_epilogue_bwd_bias_workspace_bytes(long long M, int N) {
+    size_t a = (size_t)EB_BLOCKS * N * sizeof(float), b = gb200_colsum_workspace_bytes(M, N);
+    return a > b ? a : b;
+}
+
+// g = dy * rscale * dropmask * act'(.)  AND  dbias[n] = sum_m g[m, n]   in one pass over g
+extern "C" int gb200_epilogue_bwd_bias(int device, const float* dy, int lddy, const float* z, int ldz, const float* y,
+                                       int ldy, float* g, int ldg, long long M, int N, int act, float rscale,
+                                       float drop_p, unsigned long long seed, float* dbias, float* workspace,
+                                       size_t workspace_bytes, void* stream) {
+    use_device(device);
+    GB_REQUIRE(dy && g && dbias && M >= 1 && N >= 1, "gb200_epilogue_bwd_bias: bad arguments");
+    GB_REQUIRE(workspace && workspace_bytes >= gb200_epilogue_bwd_bias_workspace_bytes(M, N),
+               "gb200_epilogue_bwd_bias: workspace too small");
+    const float* ref = z ? z : y;
+    const int ldref = z ? ldz : ldy;
+    GB_REQUIRE(act == ACT_NONE || ref, "gb200_epilogue_bwd_bias: activation backward needs z or y");
+    GB_REQUIRE(act != ACT_SILU || z, "gb200_epilogue_bwd_bias: SiLU backward needs the pre-activation");
+    auto al16 = [](const void* p) { return ((uintptr_t)p % 16) == 0; };
+    const int rowq = N / 4;
+    const bool vec = N % 4 == 0 && rowq <= 256 && 256 % rowq == 0 && lddy == N && ldg == N &&
+                     (act == ACT_NONE || ldref == N) && al16(dy) && al16(g) && (act == ACT_NONE || al16(ref)) &&
+                     al16(workspace) && M < 0x7fffffffLL / (rowq > 0 ? rowq : 1);
+    cudaStream_t st = as_stream(stream);
+    if (!vec) {
+        int rc = gb200_epilogue_bwd(device, dy, lddy, z, ldz, y, ldy, g, ldg, M, N, act, rscale, drop_p, seed, stream);
+        if (rc) return rc;
+        return gb200_colsum(device, g, ldg, M, N, 1.f, 0, dbias, workspace, workspace_bytes, stream);
+    }
+    const int rpb = 256 / rowq;
+    int blocks = cdiv(M, rpb);
+    if (blocks > EB_BLOCKS) blocks = EB_BLOCKS;
+    const float4* d4 = reinterpret_cast<const float4*>(dy);
+    const float4* r4 = reinterpret_cast<const float4*>(ref);
+    float4* g4 = reinterpret_cast<float4*>(g);
+    if (act == ACT_RELU)
+        epilogue_bwd_bias_kernel<ACT_RELU><<<blocks, 256, 0, st>>>(d4, r4, g4, (int)M, N, rscale, drop_p, seed,
+                                                                   rng_offset_ptr(), workspace);
+    else if (act == ACT_SILU)
+        epilogue_bwd_bias_kernel<ACT_SILU><<<blocks, 256, 0, st>>>(d4, r4, g4, (int)M, N, rscale, drop_p, seed,
+                                                                   rng_offset_ptr(), workspace);
+    else
+        epilogue_bwd_bias_kernel<ACT_NONE><<<blocks, 256, 0, st>>>(d4, r4, g4, (int)M, N, rscale, drop_p, seed,
+                                                                   rng_offset_ptr(), workspace);
+    colsum_final_kernel<<<cdiv(N, 32), dim3(32, 32), 0, st>>>(workspace, blocks, N, 1.f, 0, dbias);
+    return check_launch("gb200_epilogue_bwd_bias", 2);
 }

@@ -20,13 +20,17 @@
 //
 // All waits are bounded: a descriptor/protocol bug traps instead of hanging the device.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
 
 namespace gb200 {
 
-constexpr int TC_BM = 128, TC_BK = 32, TC_STAGES = 3, TC_THREADS = 192;
+constexpr int TC_BM = 128, TC_BK = 32, TC_THREADS = 192;
+// pipeline depth: 3 stages let two CTAs share an SM (one tile's epilogue overlaps another's main loop); a 6-stage,
+// one-CTA-per-SM ring for the long-K weight-gradient GEMMs was measured and is slower (tools/bench_gemm.py)
+template <bool A_MN, bool B_MN> struct TcStages { static constexpr int value = 3; };   // 6 for MN/MN measured slower
 constexpr uint32_t TC_SPIN_LIMIT = 1u << 26;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -169,6 +173,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     constexpr int A_BYTES = TC_BM * TC_BK * 4;          // 16 KB
     constexpr int B_BYTES = BN * TC_BK * 4;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int TC_STAGES = TcStages<A_MN, B_MN>::value;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by SWIZZLE_128B atoms
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -443,7 +448,7 @@ static bool make_map(CUtensorMap* m, const float* base, long long inner, long lo
 
 template <int BN, bool A_MN, bool B_MN>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& g, cudaStream_t st) {
-    constexpr int smem = TC_STAGES * (TC_BM * TC_BK * 4 + BN * TC_BK * 4) + 1024 + 256;
+    constexpr int smem = TcStages<A_MN, B_MN>::value * (TC_BM * TC_BK * 4 + BN * TC_BK * 4) + 1024 + 256;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -465,7 +470,14 @@ extern "C" int gb200_gemm_tc_supported(const float* A, int lda, const float* B, 
 }
 
 // widest N tile that still gives every SM a CTA (two co-reside per SM); narrow outputs get narrow tiles
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
 static int pick_bn(int M, int N) {
+    static const int forced = env_int("GB200_TC_BN", 0);        // tuning override (tools/bench_gemm.py)
+    if (forced && N >= forced) return forced;
     const long long mt = cdiv(M, TC_BM);
     if (N >= 128 && mt * cdiv(N, 128) >= 148) return 128;
     if (N >= 64 && mt * cdiv(N, 64) >= 148) return 64;
@@ -478,7 +490,8 @@ extern "C" int gb200_gemm_tc_suggest_ksplit(int M, int N, int K) {
     long long tiles = (long long)cdiv(M, TC_BM) * cdiv(N, bn);
     if (tiles >= 120 || K < 1024) return 1;
     int want = (int)((2 * 148 + tiles - 1) / tiles);
-    int maxs = K / 256;
+    static const int kdiv = env_int("GB200_TC_KSPLIT_DIV", 256);   // min K per split (tuning override)
+    int maxs = K / kdiv;
     int s = want < maxs ? want : maxs;
     return s < 1 ? 1 : (s > 64 ? 64 : s);
 }

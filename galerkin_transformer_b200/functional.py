@@ -177,18 +177,30 @@ class _LinearFn(torch.autograd.Function):
         dy = dy.contiguous()
         M, K = x.shape
         N = weight.shape[0]
+        dx = dw = db = None
+        want_db = has_bias and ctx.needs_input_grad[2]
         if act != 0 or drop_p > 0.0 or rscale != 1.0:
-            g = epilogue_bwd(dy, M, N, z=z, y=y, act=act, rscale=rscale, drop_p=drop_p, seed=seed)
+            if want_db:      # one pass: g and its column sums
+                lib = _lib.load()
+                g = torch.empty((M, N), dtype=torch.float32, device=dy.device)
+                db = torch.empty(N, dtype=torch.float32, device=dy.device)
+                wsb = lib.gb200_epilogue_bwd_bias_workspace_bytes(M, N)
+                ws = workspace(wsb, dy)
+                _launch("epilogue_bwd_bias", 5.0 * M * N, 4.0 * M * N * (2 + (act != 0)), lib.gb200_epilogue_bwd_bias,
+                        _dev(dy), ptr(dy), N, ptr(z), N, ptr(y), N, ptr(g), N, M, N, act, rscale, drop_p, seed, ptr(db),
+                        ptr(ws), wsb, stream_of(dy))
+                want_db = False
+            else:
+                g = epilogue_bwd(dy, M, N, z=z, y=y, act=act, rscale=rscale, drop_p=drop_p, seed=seed)
         else:
             g = dy
-        dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             gemm(g, weight, dx, M, K, N, lda=N, ldb=K, ldc=K)
         if ctx.needs_input_grad[1]:
             dw = torch.empty_like(weight)
             gemm(g, x, dw, N, K, M, lda=N, ldb=K, ldc=K, transA=True)
-        if has_bias and ctx.needs_input_grad[2]:
+        if want_db:
             db = torch.empty(N, dtype=torch.float32, device=x.device)
             colsum(g, M, N, N, db)
         dres = dy if (has_res and ctx.needs_input_grad[3]) else None
@@ -614,7 +626,16 @@ class _SpectralConvFn(torch.autograd.Function):
         dev, st = _dev(x), stream_of(x)
         halves, M2 = (2, m * m) if two_d else (1, m)
         gy = gy.contiguous()
-        gz = epilogue_bwd(gy, P, Co, z=z, act=act) if act != 0 else gy
+        dbl = None
+        if act != 0 and has_bias and ctx.needs_input_grad[3]:
+            gz = torch.empty((P, Co), dtype=torch.float32, device=x.device)
+            dbl = torch.empty(Co, dtype=torch.float32, device=x.device)
+            wsb = lib.gb200_epilogue_bwd_bias_workspace_bytes(P, Co)
+            wsp = workspace(wsb, x)
+            _launch("epilogue_bwd_bias", 5.0 * P * Co, 12.0 * P * Co, lib.gb200_epilogue_bwd_bias, dev, ptr(gy), Co,
+                    ptr(z), Co, None, Co, ptr(gz), Co, P, Co, act, 1.0, 0.0, 0, ptr(dbl), ptr(wsp), wsb, st)
+        else:
+            gz = epilogue_bwd(gy, P, Co, z=z, act=act) if act != 0 else gy
         # adjoint of the inverse transform:  dO^ = (c_ky s) * DFT(gz) on the kept modes
         if two_d:
             dZ = _ydft(gz, B * n, n, Co, m, twY, 1.0 / n, True)
@@ -628,7 +649,7 @@ class _SpectralConvFn(torch.autograd.Function):
         mix_work = (16.0 * B * halves * M2 * Ci * Co, 8.0 * halves * M2 * (2 * Ci * Co + 2 * B * (Ci + Co)))
         _launch("spectral_mix", *mix_work, lib.gb200_spectral_mix_bwd, dev, ptr(Xf), ptr(dO), ptr(fw0), ptr(fw1), B,
                 halves, M2, Ci, Co, ptr(dXf), ptr(dfw0), ptr(dfw1), 0, st)
-        dx = dxf = dwl = dbl = None
+        dx = dxf = dwl = None
         if need_dx:
             # adjoint of the forward transform + the pointwise path  gz @ Wl, one fused kernel
             wres = wl if same else torch.zeros_like(wl)
@@ -645,7 +666,7 @@ class _SpectralConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[2]:
             dwl = torch.empty_like(wl)
             gemm(gz, x, dwl, Co, Ci, P, lda=Co, ldb=Ci, ldc=Ci, transA=True)
-        if has_bias and ctx.needs_input_grad[3]:
+        if dbl is None and has_bias and ctx.needs_input_grad[3]:
             dbl = torch.empty(Co, dtype=torch.float32, device=x.device)
             colsum(gz, P, Co, Co, dbl)
         return dx, dxf, dwl, dbl, dfw0, dfw1, None, None, None

@@ -85,6 +85,13 @@ int gb200_epilogue_bwd(int device, const float* dy, int lddy, const float* z, in
                        int ldy, float* g, int ldg, long long M, int N, int act, float rscale,
                        float drop_p, unsigned long long seed, void* stream);
 
+/* same, fused with the bias gradient dbias[n] = sum_m g[m,n] (one pass over g instead of three) */
+size_t gb200_epilogue_bwd_bias_workspace_bytes(long long M, int N);
+int gb200_epilogue_bwd_bias(int device, const float* dy, int lddy, const float* z, int ldz, const float* y, int ldy,
+                            float* g, int ldg, long long M, int N, int act, float rscale, float drop_p,
+                            unsigned long long seed, float* dbias, float* workspace, size_t workspace_bytes,
+                            void* stream);
+
 /* row LayerNorm over the last dimension (post-LN encoder variant, libs/model.py:128-129, 134-135) */
 int gb200_layernorm_fwd(int device, const float* x, long long rows, int width, const float* gamma,
                         const float* beta, float eps, float* y, float* mean, float* rstd, void* stream);
