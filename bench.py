@@ -143,7 +143,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             pass
@@ -183,6 +183,26 @@ def measured_peaks():
         return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"],
                     bf16_tflops_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured")
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+def merge_gemm_layouts(summary):
+    """The tcgen05 GEMM is ONE kernel template; fold its operand-layout variants (nt / nn / tn) into one row."""
+    out = {}
+    for fam, a in summary.items():
+        key = "gemm_tc_kernel" if fam.startswith("gemm_tc_") else ("gemm_simt_kernel" if fam.startswith("gemm_simt_") else fam)
+        o = out.setdefault(key, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+        for k in o:
+            o[k] += a[k]
+    return out
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get(kernel)
+    return None
 
 
 def kernel_table(summary, steps, peaks):
@@ -388,20 +408,26 @@ def main():
         if graphed is not None:
             for p_, g_ in zip(graphed.params, graphed.static_grads):
                 p_.grad = g_
-        kernels, tf32_peak = kernel_table(GF.Profiler.summary(), prof_steps, peaks)
+        kernels, tf32_peak = kernel_table(merge_gemm_layouts(GF.Profiler.summary()), prof_steps, peaks)
+        layouts, _ = kernel_table({k: v for k, v in GF.Profiler.summary().items() if k.startswith("gemm_")},
+                                  prof_steps, peaks)
         native_ms = sum(k["ms_per_step"] for k in kernels)
         top = kernels[0]
+        traffic = ncu_traffic(top["kernel"])
         roofline = dict(kernel=top["kernel"], bound=top["bound"],
                         achieved=top["alg_tflops"] if top["bound"] == "tensor" else top["alg_gbs"],
                         peak=tf32_peak if top["bound"] == "tensor" else peaks["hbm_gbs"],
                         unit="TFLOP/s" if top["bound"] == "tensor" else "GB/s", frac=top["frac"],
-                        traffic=None, share_of_step=round(top["ms_per_step"] / ms_per_step, 4),
+                        traffic=(traffic or {}).get("dram_bytes_per_launch"), traffic_note=(traffic or {}).get("note"),
+                        alg_bytes_per_launch=top["alg_bytes_per_launch"], alg_flops_per_launch=top["alg_flops_per_launch"],
+                        alg_tflops=top["alg_tflops"], tensor_frac_of_dense_tf32=round(top["alg_tflops"] / tf32_peak, 4),
+                        share_of_step=round(top["ms_per_step"] / ms_per_step, 4), gemm_layouts=layouts,
                         peak_source=f"MEASURED_PEAKS.json ({peaks['source']}); tensor peak = sustained bf16 / 2 "
                                     "(dense TF32)",
                         timing=f"CUDA events around every launch on the launching stream, {prof_steps}-step eager "
                                "attribution pass after the timed region, launches pre-queued behind a spin kernel "
                                "so events bracket execution, not host launch latency",
-                        native_ms_per_step=round(native_ms, 3), step_ms_in_pass=round(step_ms_prof, 3))
+                        native_ms_per_step=round(native_ms, 3))
     if world > 1:
         dist.barrier()
 

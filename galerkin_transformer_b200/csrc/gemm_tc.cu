@@ -106,6 +106,7 @@ struct TcArgs {
     int ksplit, kchunk;   // kchunk is a multiple of TC_BK
     float* ws;
     int vec4;             // C/R/Z/ws rows are 16-byte aligned and N % 4 == 0: float4 epilogue
+    int truncate;         // 1: skip the round-to-nearest pass (operands truncated to TF32 by the tensor core)
 };
 
 // activation with fast intrinsics (the TF32 path is not bit-exact fp32 anyway)
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % TC_STAGES;
                 const uint32_t ph = (kb / TC_STAGES) & 1;
-                mbar_wait(&conv_bar[s], ph);     // tile landed (TMA) and rounded to TF32 (converter warps)
+                mbar_wait(g.truncate ? &full_bar[s] : &conv_bar[s], ph);   // tile landed (TMA) [and rounded to TF32]
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
                 const uint32_t sb = sa + A_BYTES;
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
         // systematic -1e-3 relative bias per product); rounding makes the error zero-mean like cuBLAS TF32.
         {
             const int ct = threadIdx.x - 64;     // 0..127
-            for (int kb = 0; kb < nkb; ++kb) {
+            for (int kb = 0; kb < (g.truncate ? 0 : nkb); ++kb) {
                 const int s = kb % TC_STAGES;
                 const uint32_t ph = (kb / TC_STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
@@ -400,6 +401,223 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Persistent variant (ksplit == 1): one CTA per SM walks a static list of output tiles.  The shared-memory ring
+// (4 stages) runs continuously across tile boundaries and the accumulator is double-buffered in TMEM, so the
+// epilogue of tile i (TMEM -> smem -> global) overlaps the TMA / convert / MMA work of tile i+1, and the fixed
+// per-CTA costs (barrier init, TMEM allocation, tensor-map fetch) are paid once per SM instead of once per tile.
+//   warp 0: TMA producer | warp 1: MMA issuer | warps 2-5: TF32 round-to-nearest converters |
+//   warps 6-13: epilogue (two warps per 32-lane TMEM quarter, each taking half of the tile's columns)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TCP_STAGES = 4, TCP_EPI_WARPS = 8, TCP_THREADS = (6 + TCP_EPI_WARPS) * 32;
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                            const __grid_constant__ CUtensorMap mapB,
+                                                                            TcArgs g) {
+    constexpr int A_BYTES = TC_BM * TC_BK * 4;
+    constexpr int B_BYTES = BN * TC_BK * 4;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int DS = BN + 4;
+    constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;      // two accumulator buffers (power of two >= 32)
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* staging = reinterpret_cast<float*>(smem + TCP_STAGES * STAGE_BYTES);            // [128][DS]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + TC_BM * DS);
+    uint64_t* empty_bar = full_bar + TCP_STAGES;
+    uint64_t* conv_bar = empty_bar + TCP_STAGES;
+    uint64_t* tmem_full = conv_bar + TCP_STAGES;       // [2]
+    uint64_t* tmem_empty = tmem_full + 2;              // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int ntn = (g.N + BN - 1) / BN, ntm = (g.M + TC_BM - 1) / TC_BM;
+    const int ntiles = ntn * ntm;
+    const int nkb = (g.K + TC_BK - 1) / TC_BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TCP_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+            mbar_init(&conv_bar[s], 4);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], TCP_EPI_WARPS);   // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {   // ---------------- TMA producer ----------------
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                const int m0 = (t / ntn) * TC_BM, n0 = (t % ntn) * BN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % TCP_STAGES;
+                    const uint32_t ph = (it / TCP_STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* sa = smem + s * STAGE_BYTES;
+                    uint8_t* sb = sa + A_BYTES;
+                    mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                    const int k0 = kb * TC_BK;
+                    if (!A_MN) {
+                        tma_load_2d(sa, &mapA, &full_bar[s], k0, m0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < TC_BM / 32; ++j) tma_load_2d(sa + j * 4096, &mapA, &full_bar[s], m0 + 32 * j, k0);
+                    }
+                    if (!B_MN) {
+                        tma_load_2d(sb, &mapB, &full_bar[s], k0, n0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * 4096, &mapB, &full_bar[s], n0 + 32 * j, k0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {   // ---------------- MMA issuer ----------------
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                                   ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                                   ((uint32_t)(TC_BM >> 4) << 24);
+            uint32_t it = 0, j = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
+                const uint32_t buf = j & 1;
+                mbar_wait(&tmem_empty[buf], ((j >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + buf * BN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % TCP_STAGES;
+                    const uint32_t ph = (it / TCP_STAGES) & 1;
+                    mbar_wait(&conv_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                    const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k) {
+                        const uint64_t ad = A_MN ? umma_desc<1>(sa + k * 1024, 4096, 512) : umma_desc<2>(sa + k * 32, 16, 1024);
+                        const uint64_t bd = B_MN ? umma_desc<1>(sb + k * 1024, 4096, 512) : umma_desc<2>(sb + k * 32, 16, 1024);
+                        tc_mma_tf32(tacc, ad, bd, idesc, (kb | k) != 0);
+                    }
+                    tc_commit(&empty_bar[s]);
+                }
+                tc_commit(&tmem_full[buf]);
+            }
+        }
+    } else if (warp < 6) {   // ---------------- converters (warps 2-5) ----------------
+        const int ct = threadIdx.x - 64;
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int s = it % TCP_STAGES;
+                const uint32_t ph = (it / TCP_STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                float4* tile = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
+#pragma unroll 4
+                for (int i = ct; i < STAGE_BYTES / 16; i += 128) {
+                    float4 v = tile[i];
+                    uint32_t x, y, z, w;
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(x) : "f"(v.x));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(y) : "f"(v.y));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(z) : "f"(v.z));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(w) : "f"(v.w));
+                    tile[i] = make_float4(__uint_as_float(x), __uint_as_float(y), __uint_as_float(z),
+                                          __uint_as_float(w));
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0)
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&conv_bar[s])) : "memory");
+            }
+        }
+    } else {                 // ---------------- epilogue (warps 6-9) ----------------
+        const int q = warp % 4;                                  // TMEM lane quarter
+        constexpr int HALF = BN >= 64 ? BN / 2 : BN;             // columns per epilogue warp
+        const int cbase = (BN >= 64 && warp >= 10) ? HALF : 0;
+        const bool idle = BN < 64 && warp >= 10;                 // 32-wide tiles: one warp per quarter is enough
+        float* stage = staging + q * 32 * DS + cbase;
+        const GemmEpilogue& ep = g.ep;
+        const unsigned long long seed = ep.seed + ((ep.drop_p > 0.f && ep.seed_off) ? *ep.seed_off : 0ull);
+        uint32_t j = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
+            const int m0 = (t / ntn) * TC_BM, n0 = (t % ntn) * BN;
+            const uint32_t buf = j & 1;
+            mbar_wait(&tmem_full[buf], (j >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < (idle ? 0 : HALF); c0 += 32) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + cbase + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                      "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+                      "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+                      "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int jj = 0; jj < 32; jj += 4)
+                    *reinterpret_cast<float4*>(&stage[lane * DS + c0 + jj]) =
+                        make_float4(__uint_as_float(v[jj]), __uint_as_float(v[jj + 1]), __uint_as_float(v[jj + 2]),
+                                    __uint_as_float(v[jj + 3]));
+            }
+            // accumulator is now in shared memory: hand the TMEM buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
+            const int nc0 = n0 + cbase;                                     // this warp's first output column
+            const int ncols = idle ? 0 : max(0, min(HALF, g.N - nc0));
+            const int rbase = m0 + q * 32;
+            if (rbase < g.M && ncols > 0) {
+                if (g.vec4) {
+                    const bool drop = ep.drop_p > 0.f;
+                    if (ep.act == ACT_NONE) {
+                        if (drop) tc_epilogue_vec4<ACT_NONE, true>(g, stage, DS, lane, rbase, nc0, ncols, seed);
+                        else tc_epilogue_vec4<ACT_NONE, false>(g, stage, DS, lane, rbase, nc0, ncols, seed);
+                    } else if (ep.act == ACT_RELU) {
+                        if (drop) tc_epilogue_vec4<ACT_RELU, true>(g, stage, DS, lane, rbase, nc0, ncols, seed);
+                        else tc_epilogue_vec4<ACT_RELU, false>(g, stage, DS, lane, rbase, nc0, ncols, seed);
+                    } else {
+                        if (drop) tc_epilogue_vec4<ACT_SILU, true>(g, stage, DS, lane, rbase, nc0, ncols, seed);
+                        else tc_epilogue_vec4<ACT_SILU, false>(g, stage, DS, lane, rbase, nc0, ncols, seed);
+                    }
+                } else {
+                    const int nrows = min(32, g.M - rbase);
+                    for (int r = 0; r < nrows; ++r)
+                        for (int c = lane; c < ncols; c += 32)
+                            ep.store(0, rbase + r, nc0 + c, g.M, g.N, stage[r * DS + c]);
+                }
+            }
+            __syncwarp();          // staging rows are rewritten by this warp for its next tile
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
 __global__ void tc_splitk_reduce_kernel(TcArgs g) {
     const long long total = (long long)g.M * g.N;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
@@ -456,6 +674,27 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs&
     }
     dim3 grid(cdiv(g.N, BN), cdiv(g.M, TC_BM), g.ksplit);
     gemm_tc_kernel<BN, A_MN, B_MN><<<grid, TC_THREADS, smem, st>>>(ma, mb, g);
+    return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_tc_persistent(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& g, cudaStream_t st) {
+    constexpr int smem = TCP_STAGES * (TC_BM * TC_BK * 4 + BN * TC_BK * 4) + TC_BM * (BN + 4) * 4 + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(gemm_tc_persistent_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = true;
+    }
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+    }
+    const int tiles = cdiv(g.N, BN) * cdiv(g.M, TC_BM);
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    gemm_tc_persistent_kernel<BN, A_MN, B_MN><<<grid, TCP_THREADS, smem, st>>>(ma, mb, g);
     return 0;
 }
 
@@ -532,12 +771,23 @@ extern "C" int gb200_gemm_tc(int device, const float* A, int lda, int transA, co
     ok = ok && (b_mn ? make_map(&mb, B, N, K, ldb, 32, 32, SWMN) : make_map(&mb, B, K, N, ldb, 32, bn, SWK));
     GB_REQUIRE(ok, "gb200_gemm_tc: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d lda=%d ldb=%d)", M, N, K, lda, ldb);
     cudaStream_t st = as_stream(stream);
-#define TC_DISPATCH(BNV)                                                               \
-    do {                                                                               \
-        if (!a_mn && !b_mn) launch_tc<BNV, false, false>(ma, mb, g, st);               \
-        else if (!a_mn && b_mn) launch_tc<BNV, false, true>(ma, mb, g, st);            \
-        else if (a_mn && !b_mn) launch_tc<BNV, true, false>(ma, mb, g, st);            \
-        else launch_tc<BNV, true, true>(ma, mb, g, st);                                \
+    static const int use_persistent = env_int("GB200_TC_PERSISTENT", 0);   // measured equal/slower in the full step
+    static const int truncate = env_int("GB200_TC_TRUNCATE", 0);
+    g.truncate = truncate;
+    const bool persistent = use_persistent && g.ksplit == 1;
+#define TC_DISPATCH(BNV)                                                                          \
+    do {                                                                                          \
+        if (persistent) {                                                                         \
+            if (!a_mn && !b_mn) launch_tc_persistent<BNV, false, false>(ma, mb, g, st);           \
+            else if (!a_mn && b_mn) launch_tc_persistent<BNV, false, true>(ma, mb, g, st);        \
+            else if (a_mn && !b_mn) launch_tc_persistent<BNV, true, false>(ma, mb, g, st);        \
+            else launch_tc_persistent<BNV, true, true>(ma, mb, g, st);                            \
+        } else {                                                                                  \
+            if (!a_mn && !b_mn) launch_tc<BNV, false, false>(ma, mb, g, st);                      \
+            else if (!a_mn && b_mn) launch_tc<BNV, false, true>(ma, mb, g, st);                   \
+            else if (a_mn && !b_mn) launch_tc<BNV, true, false>(ma, mb, g, st);                   \
+            else launch_tc<BNV, true, true>(ma, mb, g, st);                                       \
+        }                                                                                         \
     } while (0)
     if (bn == 128) TC_DISPATCH(128);
     else if (bn == 64) TC_DISPATCH(64);
