@@ -14,6 +14,7 @@
 //   libs/layers.py:723, 728, 733      K^T V, /n, Q.(.)           (linear_attention)
 //   libs/layers.py:730-731            F.dropout(p_attn), p=0.5, always on (mask input)
 //   libs/layers.py:892-894            transpose(1,2).contiguous().view  (head merge)
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace gb200 {
@@ -504,11 +505,11 @@ extern "C" int gb200_headnorm_bwd(int device, float* dy, int lddy, int dcol0, in
 }
 
 extern "C" int gb200_attn_suggest_nsplit(int B, int H, int n) {
-    int bh = B * H;
-    int want = (2 * 148) / bh;          // one wave at two resident CTAs per SM
-    if (want < 1) want = 1;
-    int maxs = (n + 63) / 64;
-    int s = want < maxs ? want : maxs;
+    // The kernel is latency-bound (stage tokens -> sync -> contract): give every 64-token stage its own CTA so all
+    // loads of the launch are in flight at once, instead of a few CTAs looping over stages.  Tunable for A/B runs.
+    static const int per = []() { const char* v = getenv("GB200_XTY_TOKENS_PER_CTA"); return v ? atoi(v) : 64; }();
+    int s = (n + per - 1) / per;
+    if (s > 64) s = 64;
     return s < 1 ? 1 : s;
 }
 

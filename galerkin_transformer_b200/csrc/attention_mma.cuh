@@ -61,10 +61,10 @@ __device__ __forceinline__ void stage_aug(float* __restrict__ S, const HeadOpera
 
 // ---- xty: P[i][j] = sum_t L~[t][i] R~[t][j];  MT x NT tiles of 16 x 8, i < 16*MT, j < 8*NT --------------
 template <int MT, int NT>
-__global__ void __launch_bounds__(256, (MT * NT <= 15) ? 2 : 1) xty_mma_kernel(HeadOperand L, HeadOperand R, const float* __restrict__ pos,
+__global__ void __launch_bounds__(256, 3) xty_mma_kernel(HeadOperand L, HeadOperand R, const float* __restrict__ pos,
                                                       int p, int dk, int H, int n, int nsplit, int chunk,
                                                       float* __restrict__ part) {
-    constexpr int TC = 64;                         // tokens per stage: 8 warps x 8 tokens (one k-step each)
+    constexpr int TC = 64;                         // tokens per stage (8 k-steps of the m16n8k8 MMA)
     constexpr int DM = 16 * MT, DN = 8 * NT;
     constexpr int LS = DM + 8 - (DM % 32 == 8 ? 0 : 0), RS = DN;   // pitches: see bank note below
     // fragment reads index [token = t0 + (lane%4)(+4)][feature = f0 + lane/4]; pitch = 8 (mod 32) makes the
@@ -78,63 +78,52 @@ __global__ void __launch_bounds__(256, (MT * NT <= 15) ? 2 : 1) xty_mma_kernel(H
     const int bh = blockIdx.y, b = bh / H, h = bh % H, split = blockIdx.x;
     const int tbeg = split * chunk, tend = min(n, tbeg + chunk);
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, g = lane / 4, tq = lane % 4;
-    float acc[MT][NT][4];
+    // Warps split the OUTPUT tiles (tile = warp, warp + 8, ...) and each contracts all staged tokens: no
+    // cross-warp reduction, a handful of accumulator registers per thread.
+    constexpr int TILES = MT * NT, SLOTS = (TILES + 7) / 8;
+    float acc[SLOTS][4];
 #pragma unroll
-    for (int a = 0; a < MT; ++a)
+    for (int sl = 0; sl < SLOTS; ++sl)
 #pragma unroll
-        for (int c = 0; c < NT; ++c)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) acc[a][c][k] = 0.f;
+        for (int k = 0; k < 4; ++k) acc[sl][k] = 0.f;
 
     for (int t0 = tbeg; t0 < tend; t0 += TC) {
         const int nt = min(TC, tend - t0);
         stage_aug<DM, LP, 256, TC>(&Ls[0][0], L, pos, p, dk, h, (long long)b * n + t0, nt);
         stage_aug<DN, RP, 256, TC>(&Rs[0][0], R, pos, p, dk, h, (long long)b * n + t0, nt);
         __syncthreads();
-        const int tk = warp * 8;                    // this warp's 8 tokens of the stage
-        float bf[NT][2];
 #pragma unroll
-        for (int c = 0; c < NT; ++c) {
-            bf[c][0] = Rs[tk + tq][8 * c + g];
-            bf[c][1] = Rs[tk + tq + 4][8 * c + g];
-        }
+        for (int sl = 0; sl < SLOTS; ++sl) {
+            const int tile = warp + 8 * sl;
+            if (tile < TILES) {
+                const int a = tile / NT, c = tile % NT;
 #pragma unroll
-        for (int a = 0; a < MT; ++a) {
-            float af[4];
-            af[0] = Ls[tk + tq][16 * a + g];
-            af[1] = Ls[tk + tq][16 * a + g + 8];
-            af[2] = Ls[tk + tq + 4][16 * a + g];
-            af[3] = Ls[tk + tq + 4][16 * a + g + 8];
-#pragma unroll
-            for (int c = 0; c < NT; ++c) mma_tf32(acc[a][c], af, bf[c]);
-        }
-        __syncthreads();
-    }
-    // cross-warp sum in fixed order through shared memory (reuses the L tile), then the partial
-    float* red = &Ls[0][0];                         // needs DM*DN floats <= TC*LP
-    static_assert(DM * DN <= TC * LP, "reduction buffer does not fit");
-    for (int w = 0; w < 8; ++w) {
-        if (warp == w) {
-#pragma unroll
-            for (int a = 0; a < MT; ++a)
-#pragma unroll
-                for (int c = 0; c < NT; ++c) {
-                    const int i0 = 16 * a + g, j0 = 8 * c + 2 * tq;
-                    float* r0 = red + i0 * DN + j0;
-                    float* r1 = red + (i0 + 8) * DN + j0;
-                    if (w == 0) {
-                        r0[0] = acc[a][c][0]; r0[1] = acc[a][c][1]; r1[0] = acc[a][c][2]; r1[1] = acc[a][c][3];
-                    } else {
-                        r0[0] += acc[a][c][0]; r0[1] += acc[a][c][1]; r1[0] += acc[a][c][2]; r1[1] += acc[a][c][3];
-                    }
+                for (int ks = 0; ks < TC / 8; ++ks) {
+                    const int tk = 8 * ks;
+                    float af[4], bf[2];
+                    af[0] = Ls[tk + tq][16 * a + g];
+                    af[1] = Ls[tk + tq][16 * a + g + 8];
+                    af[2] = Ls[tk + tq + 4][16 * a + g];
+                    af[3] = Ls[tk + tq + 4][16 * a + g + 8];
+                    bf[0] = Rs[tk + tq][8 * c + g];
+                    bf[1] = Rs[tk + tq + 4][8 * c + g];
+                    mma_tf32(acc[sl], af, bf);
                 }
+            }
         }
         __syncthreads();
     }
     float* out = part + ((long long)bh * nsplit + split) * d * d;
-    for (int e = threadIdx.x; e < d * d; e += 256) {
-        const int i = e / d, j = e % d;
-        out[e] = red[i * DN + j];
+#pragma unroll
+    for (int sl = 0; sl < SLOTS; ++sl) {
+        const int tile = warp + 8 * sl;
+        if (tile >= TILES) continue;
+        const int a = tile / NT, c = tile % NT;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = 16 * a + g + (k >= 2 ? 8 : 0), j = 8 * c + 2 * tq + (k & 1);
+            if (i < d && j < d) out[i * d + j] = acc[sl][k];
+        }
     }
 }
 

@@ -15,6 +15,11 @@ struct GemmEpilogue {
     const unsigned long long* seed_off;   // device-side step counter (or null): seed += *seed_off
     const float* R; int ldr; float rscale;
     int accumulate;
+    // fused per-head LayerNorm statistics (tcgen05 float4 epilogue only): columns [hn_lo, hn_hi) are split into
+    // groups of hn_dk; each group of a row is replaced by (v - mean) * rstd and rstd goes to hn_rstd[block][row, head]
+    int hn_dk, hn_lo, hn_hi, hn_heads;
+    float hn_eps;
+    float* hn_rstd[2];
 
     __device__ __forceinline__ void store(int batch, int m, int n, int M, int N, float acc) const {
         float v = alpha * acc;

@@ -302,6 +302,7 @@ extern "C" int gb200_gemm(int device, const float* A, int lda, int transA, const
     g.kchunk = cdiv(ktiles, ksplit) * BK;
     g.ep.alpha = alpha; g.ep.bias = bias; g.ep.act = act; g.ep.Z = Zout; g.ep.ldz = ldz; g.ep.drop_p = drop_p;
     g.ep.seed = seed; g.ep.seed_off = rng_offset_ptr(); g.ep.R = R; g.ep.ldr = ldr; g.ep.rscale = rscale; g.ep.accumulate = accumulate;
+    g.ep.hn_dk = 0; g.ep.hn_lo = g.ep.hn_hi = g.ep.hn_heads = 0; g.ep.hn_eps = 0.f; g.ep.hn_rstd[0] = g.ep.hn_rstd[1] = nullptr;
     g.ws = workspace;
     g.vecA = ((uintptr_t)A % 16 == 0) && (lda % 4 == 0) && (strideA % 4 == 0);
     g.vecB = ((uintptr_t)B % 16 == 0) && (ldb % 4 == 0) && (strideB % 4 == 0);

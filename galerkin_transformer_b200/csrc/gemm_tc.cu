@@ -119,7 +119,7 @@ __device__ __forceinline__ float act_fast(float v) {
 
 // Coalesced float4 epilogue for one warp's 32 accumulator rows staged in shared memory.
 // Compile-time activation / dropout; residual, Z and accumulate are warp-uniform runtime switches.
-template <int ACT, bool DROP>
+template <int ACT, bool DROP, bool HN = false>
 __device__ __forceinline__ void tc_epilogue_vec4(const TcArgs& g, const float* __restrict__ stage, int DS, int lane,
                                                  int rbase, int n0, int ncols, unsigned long long seed) {
     const GemmEpilogue& ep = g.ep;
@@ -127,10 +127,16 @@ __device__ __forceinline__ void tc_epilogue_vec4(const TcArgs& g, const float* _
     const bool hasR = ep.R != nullptr, hasZ = ep.Z != nullptr, accum = ep.accumulate != 0;
     const float alpha = ep.alpha, rscale = ep.rscale, p = ep.drop_p;
     const int nrows = min(32, g.M - rbase);
-    for (int c = lane * 4; c < ncols; c += 128) {
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    // warp-uniform trip counts (the fused head-norm shuffles need every lane): columns past ncols are predicated
+    // (only the fused head-norm variant needs warp-uniform trip counts for its shuffles; the plain epilogue keeps the
+    // cheaper per-lane loop)
+    for (int cb = HN ? 0 : lane * 4; cb < ncols; cb += 128) {
+        const int c = HN ? cb + lane * 4 : cb;
+        const bool cv = HN ? (c < ncols) : true;
         const int n = n0 + c;
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ep.bias) bv = *reinterpret_cast<const float4*>(ep.bias + n);
+        float4 bv = zero4;
+        if (cv && ep.bias) bv = *reinterpret_cast<const float4*>(ep.bias + n);
         const float* rp = hasR ? ep.R + (long long)rbase * ep.ldr + n : nullptr;
         float* cp = ep.C + (long long)rbase * ep.ldc + n;
         float* zp = hasZ ? ep.Z + (long long)rbase * ep.ldz + n : nullptr;
@@ -139,21 +145,44 @@ __device__ __forceinline__ void tc_epilogue_vec4(const TcArgs& g, const float* _
             float4 acc[RB], rv[RB];
 #pragma unroll
             for (int i = 0; i < RB; ++i) {
-                acc[i] = *reinterpret_cast<const float4*>(&stage[(r0 + i) * DS + c]);
-                rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (r0 + i < nrows) {
+                acc[i] = cv ? *reinterpret_cast<const float4*>(&stage[(r0 + i) * DS + c]) : zero4;
+                rv[i] = zero4;
+                if (cv && r0 + i < nrows) {
                     if (hasR) rv[i] = *reinterpret_cast<const float4*>(rp + (long long)(r0 + i) * ep.ldr);
                     if (accum) {
-                        const float4 cv = *reinterpret_cast<const float4*>(cp + (long long)(r0 + i) * ep.ldc);
-                        rv[i].x += cv.x; rv[i].y += cv.y; rv[i].z += cv.z; rv[i].w += cv.w;
+                        const float4 cvv = *reinterpret_cast<const float4*>(cp + (long long)(r0 + i) * ep.ldc);
+                        rv[i].x += cvv.x; rv[i].y += cvv.y; rv[i].z += cvv.z; rv[i].w += cvv.w;
                     }
                 }
             }
 #pragma unroll
             for (int i = 0; i < RB; ++i) {
-                if (r0 + i >= nrows) break;
+                if (r0 + i >= nrows) break;                                  // uniform across the warp
                 float4 z = make_float4(fmaf(alpha, acc[i].x, bv.x), fmaf(alpha, acc[i].y, bv.y),
                                        fmaf(alpha, acc[i].z, bv.z), fmaf(alpha, acc[i].w, bv.w));
+                if (HN) {
+                    // per-head LayerNorm statistics over the hn_dk columns of this row's head group (hn_dk / 4 lanes)
+                    const int lg = ep.hn_dk >> 2;
+                    float sm = z.x + z.y + z.z + z.w;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1)
+                        if (o < lg) sm += __shfl_xor_sync(0xffffffffu, sm, o);      // lg is warp-uniform
+                    const float mean = sm / ep.hn_dk;
+                    const float dx = z.x - mean, dy = z.y - mean, dz = z.z - mean, dw = z.w - mean;
+                    float sq = dx * dx + dy * dy + dz * dz + dw * dw;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1)
+                        if (o < lg) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                    const float rs = rsqrtf(sq / ep.hn_dk + ep.hn_eps);
+                    if (cv && n >= ep.hn_lo && n < ep.hn_hi) {
+                        z = make_float4(dx * rs, dy * rs, dz * rs, dw * rs);
+                        if ((lane & (lg - 1)) == 0) {
+                            const int rel = n - ep.hn_lo, blkw = ep.hn_heads * ep.hn_dk;
+                            ep.hn_rstd[rel / blkw][(long long)(rbase + r0 + i) * ep.hn_heads + (rel % blkw) / ep.hn_dk] = rs;
+                        }
+                    }
+                }
+                if (!cv) continue;
                 if (hasZ) *reinterpret_cast<float4*>(zp + (long long)(r0 + i) * ep.ldz) = z;
                 float4 v = make_float4(act_fast<ACT>(z.x), act_fast<ACT>(z.y), act_fast<ACT>(z.z), act_fast<ACT>(z.w));
                 if (DROP) {
@@ -349,7 +378,9 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
                         *reinterpret_cast<const float4*>(&stage[r * DS + c]);
         } else if (g.vec4) {
             const bool drop = ep.drop_p > 0.f;
-            if (ep.act == ACT_NONE) {
+            if (ep.hn_dk) {        // QKV projection with fused per-head LayerNorm (host guarantees act none, no dropout)
+                tc_epilogue_vec4<ACT_NONE, false, true>(g, stage, DS, lane, rbase, n0, ncols, seed);
+            } else if (ep.act == ACT_NONE) {
                 if (drop) tc_epilogue_vec4<ACT_NONE, true>(g, stage, DS, lane, rbase, n0, ncols, seed);
                 else tc_epilogue_vec4<ACT_NONE, false>(g, stage, DS, lane, rbase, n0, ncols, seed);
             } else if (ep.act == ACT_RELU) {
@@ -735,6 +766,11 @@ extern "C" int gb200_gemm_tc_suggest_ksplit(int M, int N, int K) {
     return s < 1 ? 1 : (s > 64 ? 64 : s);
 }
 
+namespace gb200 {
+struct HeadNormFusion { int dk, lo, hi, heads; float eps; float* rstd[2]; };
+static thread_local HeadNormFusion g_hn = {0, 0, 0, 0, 0.f, {nullptr, nullptr}};
+}
+
 extern "C" int gb200_gemm_tc(int device, const float* A, int lda, int transA, const float* B, int ldb, int transB,
                              float* C, int ldc, int M, int N, int K, float alpha, const float* bias, int act,
                              float* Zout, int ldz, float drop_p, unsigned long long seed, const float* R, int ldr,
@@ -755,6 +791,8 @@ extern "C" int gb200_gemm_tc(int device, const float* A, int lda, int transA, co
     g.ep.C = C; g.ep.ldc = ldc; g.ep.sC = 0; g.ep.alpha = alpha; g.ep.bias = bias; g.ep.act = act; g.ep.Z = Zout;
     g.ep.ldz = ldz; g.ep.drop_p = drop_p; g.ep.seed = seed; g.ep.seed_off = rng_offset_ptr(); g.ep.R = R; g.ep.ldr = ldr; g.ep.rscale = rscale;
     g.ep.accumulate = accumulate;
+    g.ep.hn_dk = g_hn.dk; g.ep.hn_lo = g_hn.lo; g.ep.hn_hi = g_hn.hi; g.ep.hn_heads = g_hn.heads; g.ep.hn_eps = g_hn.eps;
+    g.ep.hn_rstd[0] = g_hn.rstd[0]; g.ep.hn_rstd[1] = g_hn.rstd[1];
     g.M = M; g.N = N; g.K = K; g.ksplit = ksplit;
     g.kchunk = cdiv(cdiv(K, TC_BK), ksplit) * TC_BK;
     g.ksplit = cdiv(K, g.kchunk);
@@ -765,6 +803,7 @@ extern "C" int gb200_gemm_tc(int device, const float* A, int lda, int transA, co
     if (g.ksplit > 1)
         GB_REQUIRE(workspace && workspace_bytes >= (size_t)g.ksplit * M * N * sizeof(float),
                    "gb200_gemm_tc: split-K workspace too small");
+    GB_REQUIRE(!g.ep.hn_dk || (g.vec4 && g.ksplit == 1), "gb200_gemm_tc: fused head-norm needs the float4 epilogue");
     CUtensorMap ma, mb;
     const CUtensorMapSwizzle SWK = CU_TENSOR_MAP_SWIZZLE_128B, SWMN = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
     bool ok = a_mn ? make_map(&ma, A, M, K, lda, 32, 32, SWMN) : make_map(&ma, A, K, M, lda, 32, TC_BM, SWK);
@@ -774,7 +813,7 @@ extern "C" int gb200_gemm_tc(int device, const float* A, int lda, int transA, co
     static const int use_persistent = env_int("GB200_TC_PERSISTENT", 0);   // measured equal/slower in the full step
     static const int truncate = env_int("GB200_TC_TRUNCATE", 0);
     g.truncate = truncate;
-    const bool persistent = use_persistent && g.ksplit == 1;
+    const bool persistent = use_persistent && g.ksplit == 1 && !g.ep.hn_dk;
 #define TC_DISPATCH(BNV)                                                                          \
     do {                                                                                          \
         if (persistent) {                                                                         \
@@ -800,4 +839,29 @@ extern "C" int gb200_gemm_tc(int device, const float* A, int lda, int transA, co
         tc_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(g);
     }
     return check_launch("gb200_gemm_tc", g.ksplit > 1 ? 2 : 1);
+}
+
+/* y = x W^T + b with per-head LayerNorm statistics fused into the epilogue: columns [col_lo, col_hi) of the output
+ * (two operand blocks of heads*dk columns each, e.g. K and V of the packed Q|K|V projection) are replaced by
+ * (y - mean) * rstd per (row, head) and rstd is written to rstd_a / rstd_b (rows, heads).
+ * libs/layers.py:837-839 + 846-851 in one kernel.  Requirements beyond gb200_gemm_tc: no activation / dropout /
+ * residual / split-K, N % 4 == 0, dk % 4 == 0 with dk/4 a power of two <= 32, 32 % (dk/4) == 0, col_lo % dk == 0. */
+extern "C" int gb200_gemm_tc_headnorm(int device, const float* A, int lda, const float* W, int ldw, float* C, int ldc,
+                                      int M, int N, int K, const float* bias, int col_lo, int col_hi, int heads, int dk,
+                                      float eps, float* rstd_a, float* rstd_b, void* stream) {
+    const int lg = dk / 4;
+    GB_REQUIRE(dk % 4 == 0 && lg >= 1 && lg <= 32 && (lg & (lg - 1)) == 0, "gb200_gemm_tc_headnorm: unsupported d_k=%d", dk);
+    GB_REQUIRE(col_lo % dk == 0 && (col_hi - col_lo) % (heads * dk) == 0 && col_hi <= N && col_lo >= 0 &&
+                   (col_hi - col_lo) / (heads * dk) >= 1 && (col_hi - col_lo) / (heads * dk) <= 2,
+               "gb200_gemm_tc_headnorm: bad column range [%d, %d)", col_lo, col_hi);
+    GB_REQUIRE(rstd_a && ((col_hi - col_lo) / (heads * dk) == 1 || rstd_b), "gb200_gemm_tc_headnorm: null rstd");
+    GB_REQUIRE(N % 128 == 0 || N == 64 || N == 32, "gb200_gemm_tc_headnorm: N=%d must tile evenly", N);
+    GB_REQUIRE(N % 4 == 0 && ldc % 4 == 0 && ((uintptr_t)C % 16) == 0 && (!bias || ((uintptr_t)bias % 16) == 0),
+               "gb200_gemm_tc_headnorm: output must be float4-aligned");
+    g_hn.dk = dk; g_hn.lo = col_lo; g_hn.hi = col_hi; g_hn.heads = heads; g_hn.eps = eps;
+    g_hn.rstd[0] = rstd_a; g_hn.rstd[1] = rstd_b;
+    int rc = gb200_gemm_tc(device, A, lda, 0, W, ldw, 1, C, ldc, M, N, K, 1.f, bias, ACT_NONE, nullptr, 0, 0.f, 0, nullptr,
+                           0, 1.f, 0, 1, nullptr, 0, stream);
+    g_hn.dk = 0;
+    return rc;
 }

@@ -18,6 +18,10 @@ ACT = {"none": 0, None: 0, "identity": 0, "relu": 1, "silu": 2}
 # GEMM arithmetic: "tf32" = tcgen05 tensor cores (fp32 storage, TF32 multiplies, fp32 accumulate);
 # "fp32" = exact-fp32 SIMT FMAs everywhere (the precise mode used by the tight parity tests).
 _PRECISION = "tf32"
+# fold the K,V per-head LayerNorm statistics into the Q|K|V projection's tcgen05 epilogue (A/B switch)
+# -- measured 0.17 ms/step SLOWER at C3 than the separate coalesced headnorm kernel (the epilogue runs on 4 warps per
+# CTA, the stand-alone kernel on the whole GPU), so it is opt-in: GB200_FUSE_HEADNORM=1
+_FUSE_HEADNORM = __import__("os").environ.get("GB200_FUSE_HEADNORM", "0") == "1"
 
 
 def set_precision(mode):
@@ -339,16 +343,25 @@ class _LinearAttentionFn(torch.autograd.Function):
         tc = int(_PRECISION == "tf32")
         qkv = torch.empty((T, 3 * dm), dtype=torch.float32, device=query.device)
         xs = [t.reshape(T, dm) for t in (query, key, value)]
-        if self_attn:      # one GEMM, N = 3*d_model
+        blocks = {"kv": (1, 2), "qk": (1, 0), None: ()}[norm_on]
+        lgq = dk // 4
+        fuse_norm = (_FUSE_HEADNORM and self_attn and _PRECISION == "tf32" and norm_on == "kv" and dk % 4 == 0 and 1 <= lgq <= 32
+                     and (lgq & (lgq - 1)) == 0 and (3 * dm) % 128 == 0 and dm % 4 == 0
+                     and lib.gb200_gemm_tc_supported(ptr(xs[0]), dm, ptr(wqkv), dm, T, 3 * dm, dm))
+        rstd = []
+        if fuse_norm:      # one tcgen05 GEMM: Q|K|V projection with the K,V per-head LayerNorm statistics in its epilogue
+            rstd = [torch.empty((T, H), dtype=torch.float32, device=query.device) for _ in blocks]
+            _launch("gemm_tc_nt", 2.0 * T * 3 * dm * dm, 4.0 * (T * dm + 3 * dm * dm + T * 3 * dm),
+                    lib.gb200_gemm_tc_headnorm, dev, ptr(xs[0]), dm, ptr(wqkv), dm, ptr(qkv), 3 * dm, T, 3 * dm, dm,
+                    ptr(bqkv), dm, 3 * dm, H, dk, eps, ptr(rstd[0]), ptr(rstd[1]), st)
+        elif self_attn:      # one GEMM, N = 3*d_model
             gemm(xs[0], wqkv, qkv, T, 3 * dm, dm, lda=dm, ldb=dm, ldc=3 * dm, transB=True, bias=bqkv)
         else:
             for i in range(3):
                 gemm(xs[i], wqkv, qkv, T, dm, dm, lda=dm, ldb=dm, ldc=3 * dm, transB=True,
                      bias=bqkv[i * dm:(i + 1) * dm], b_off=i * dm * dm, c_off=i * dm)
         # which blocks are normalised: galerkin -> (K, V), fourier -> (Q, K)
-        blocks = {"kv": (1, 2), "qk": (1, 0), None: ()}[norm_on]
-        rstd = []
-        if blocks:      # both normalised operand blocks in ONE launch
+        if blocks and not fuse_norm:      # both normalised operand blocks in ONE launch
             rstd = [torch.empty((T, H), dtype=torch.float32, device=query.device) for _ in blocks]
             _launch("headnorm_fwd", 16.0 * T * dm, 16.0 * T * dm, lib.gb200_headnorm_fwd, dev, ptr(qkv), 3 * dm,
                     blocks[0] * dm, blocks[1] * dm, T, H, dk, eps, ptr(rstd[0]), ptr(rstd[1]), st)

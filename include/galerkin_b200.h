@@ -74,6 +74,14 @@ int gb200_gemm_tc(int device, const float* A, int lda, int transA, const float* 
                   float rscale, int accumulate, int ksplit, float* workspace, size_t workspace_bytes,
                   void* stream);
 
+/* C = A W^T + bias on the tensor cores with per-head LayerNorm statistics fused into the epilogue: output columns
+ * [col_lo, col_hi) -- one or two operand blocks of heads*dk columns, e.g. K and V of the packed Q|K|V projection --
+ * are replaced by (y - mean) * rstd per (row, head); rstd goes to rstd_a / rstd_b (rows, heads).
+ * libs/layers.py:837-839 + 846-851 in one kernel (the affine part is applied on load by the attention kernels). */
+int gb200_gemm_tc_headnorm(int device, const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N,
+                           int K, const float* bias, int col_lo, int col_hi, int heads, int dk, float eps,
+                           float* rstd_a, float* rstd_b, void* stream);
+
 /* out[n] (+)= scale * sum_m X[m,n]            (bias gradients) */
 size_t gb200_colsum_workspace_bytes(long long M, int N);
 int gb200_colsum(int device, const float* X, int ld, long long M, int N, float scale, int accumulate,
