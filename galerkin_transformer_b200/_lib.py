@@ -34,6 +34,7 @@ SIGNATURES = {
     "gb200_last_error": (ctypes.c_char_p, []),
     "gb200_launch_count": (c_ull, []),
     "gb200_set_rng_offset_ptr": (c_int, [c_vp]),
+    "gb200_pack": (c_int, [c_int, c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_ll), c_int, c_vp]),
     "gb200_gemm_workspace_bytes": (c_sz, [c_int] * 5),
     "gb200_gemm_suggest_ksplit": (c_int, [c_int] * 4),
     "gb200_gemm": (c_int, [c_int, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_int,

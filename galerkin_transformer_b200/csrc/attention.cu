@@ -16,29 +16,7 @@
 //   libs/layers.py:892-894            transpose(1,2).contiguous().view  (head merge)
 #include <stdlib.h>
 #include "common.cuh"
-
-namespace gb200 {
-
-struct HeadOperand {
-    const float* ptr;    // token-major rows
-    int ld;              // row stride (floats)
-    int col0;            // first column of head 0
-    int augmented;       // 1: rows already hold [pos | x] per head (stride d per head)
-    const float* gamma;  // (H, d_k) or null
-    const float* beta;   // (H, d_k) or null
-};
-
-__device__ __forceinline__ float load_aug(const HeadOperand& op, const float* __restrict__ pos, int p,
-                                          int dk, int h, long long t, int i) {
-    if (op.augmented) return op.ptr[t * op.ld + op.col0 + h * (p + dk) + i];
-    if (i < p) return pos[t * p + i];
-    const int c = i - p;
-    float v = op.ptr[t * op.ld + op.col0 + h * dk + c];
-    if (op.gamma) v = v * op.gamma[h * dk + c] + op.beta[h * dk + c];
-    return v;
-}
-
-}  // namespace gb200
+#include "head_operand.cuh"
 #include "attention_mma.cuh"
 namespace gb200 {
 
@@ -399,12 +377,7 @@ static int pick_dp(int d) { return d <= 32 ? 32 : d <= 64 ? 64 : d <= 128 ? 128 
 
 using namespace gb200;
 
-static HeadOperand make_op(const gb200_head_operand* o) {
-    HeadOperand h;
-    h.ptr = o->ptr; h.ld = o->ld; h.col0 = o->col0; h.augmented = o->augmented;
-    h.gamma = o->gamma; h.beta = o->beta;
-    return h;
-}
+static HeadOperand make_op(const gb200_head_operand* o) { return make_head_operand(o); }
 
 extern "C" int gb200_headnorm_fwd(int device, float* x, int ld, int col0, int col0b, long long T, int H, int dk,
                                   float eps, float* rstd, float* rstd_b, void* stream) {

@@ -12,22 +12,9 @@
 //     dSp = c * drop (.) (dO V~^T)        dQ~ = dSp K~        dK~ = dSp^T Q~
 // Exact fp32 FMAs (this is the precise path; a tcgen05 version of this tensor-bound kernel is the next step).
 #include "common.cuh"
+#include "head_operand.cuh"
 
 namespace gb200 {
-
-struct HeadOperand {
-    const float* ptr; int ld; int col0; int augmented; const float* gamma; const float* beta;
-};
-
-__device__ __forceinline__ float quad_load(const HeadOperand& op, const float* __restrict__ pos, int p, int dk, int h,
-                                           long long t, int i) {
-    if (op.augmented) return op.ptr[t * op.ld + op.col0 + h * (p + dk) + i];
-    if (i < p) return pos[t * p + i];
-    const int c = i - p;
-    float v = op.ptr[t * op.ld + op.col0 + h * dk + c];
-    if (op.gamma) v = v * op.gamma[h * dk + c] + op.beta[h * dk + c];
-    return v;
-}
 
 constexpr int QT = 64;     // tile rows (queries and keys)
 
@@ -49,7 +36,7 @@ __device__ __forceinline__ void load_tile(float* __restrict__ S, const HeadOpera
     const int d = a.p + a.dk;
     for (int e = threadIdx.x; e < QT * DP; e += blockDim.x) {
         const int r = e / DP, i = e % DP;
-        S[r * (DP + 1) + i] = (r < nt && i < d) ? quad_load(op, a.pos, a.p, a.dk, h, tok0 + r, i) : 0.f;
+        S[r * (DP + 1) + i] = (r < nt && i < d) ? load_aug(op, a.pos, a.p, a.dk, h, tok0 + r, i) : 0.f;
     }
 }
 
@@ -211,12 +198,7 @@ __global__ void __launch_bounds__(256) quad_cols_kernel(QuadArgs a) {
 
 using namespace gb200;
 
-static HeadOperand mk(const gb200_head_operand* o) {
-    HeadOperand h;
-    if (!o) { h.ptr = nullptr; h.ld = 0; h.col0 = 0; h.augmented = 0; h.gamma = nullptr; h.beta = nullptr; return h; }
-    h.ptr = o->ptr; h.ld = o->ld; h.col0 = o->col0; h.augmented = o->augmented; h.gamma = o->gamma; h.beta = o->beta;
-    return h;
-}
+static HeadOperand mk(const gb200_head_operand* o) { return make_head_operand(o); }
 
 static int quad_common(QuadArgs& a, const gb200_head_operand* q, const gb200_head_operand* k,
                        const gb200_head_operand* v, const gb200_head_operand* dO, const float* pos, int B, int H, int n,

@@ -152,6 +152,42 @@ def epilogue_bwd(dy, M, N, *, z=None, y=None, act=0, rscale=1.0, drop_p=0.0, see
 
 
 # ------------------------------------------------------------------------------------------
+# parameter packing
+# ------------------------------------------------------------------------------------------
+class _PackFn(torch.autograd.Function):
+    """flat = concat(t.reshape(-1) for t in tensors) in ONE kernel; backward hands each parameter a view of the
+    incoming flat gradient (no kernels)."""
+
+    @staticmethod
+    def forward(ctx, *tensors):
+        require_cuda_f32(*tensors)
+        import ctypes
+        n = len(tensors)
+        ts = [t if t.is_contiguous() else t.contiguous() for t in tensors]
+        sizes = [t.numel() for t in ts]
+        flat = torch.empty(sum(sizes), dtype=torch.float32, device=ts[0].device)
+        srcs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts])
+        szs = (ctypes.c_longlong * n)(*sizes)
+        _launch("pack", 0.0, 8.0 * sum(sizes), _lib.load().gb200_pack, _dev(flat), ptr(flat), srcs, szs, n,
+                stream_of(flat))
+        ctx.shapes = [t.shape for t in tensors]
+        ctx.sizes = sizes
+        return flat
+
+    @staticmethod
+    def backward(ctx, g):
+        out, off = [], 0
+        for shape, n in zip(ctx.shapes, ctx.sizes):
+            out.append(g[off:off + n].view(shape))
+            off += n
+        return tuple(out)
+
+
+def pack(tensors):
+    return _PackFn.apply(*tensors)
+
+
+# ------------------------------------------------------------------------------------------
 # Linear (+bias, activation, fused dropout, signed residual)
 # ------------------------------------------------------------------------------------------
 class _LinearFn(torch.autograd.Function):
@@ -332,11 +368,12 @@ class _LinearAttentionFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, query, key, value, pos, wqkv, bqkv, g1, b1, g2, b2, keep_mask, cfg):
+    def forward(ctx, query, key, value, pos, flat, keep_mask, cfg):
         H, dk, p, eps, norm_on, scale, self_attn, mask_p, mask_seed, quadratic, want_attn = cfg
-        require_cuda_f32(query, key, value, pos, wqkv, bqkv, g1, b1, g2, b2)
+        require_cuda_f32(query, key, value, pos, flat)
         lib = _lib.load()
         B, n, dm = query.shape
+        wqkv, bqkv, g1, b1, g2, b2 = _unpack_attention_params(flat, dm, H, dk, norm_on is not None)
         T, d = B * n, dk + p
         dev = _dev(query)
         st = stream_of(query)
@@ -377,7 +414,7 @@ class _LinearAttentionFn(torch.autograd.Function):
             _launch("fourier_quad_fwd", 4.0 * B * H * n * n * d, 4.0 * (3 * T * dm + T * H * d),
                     lib.gb200_fourier_quad_fwd, dev, ops[0], ops[1], ops[2], ptr(pos), B, H, n, dk, p, scale,
                     ptr(keep_mask), mask_p, mask_seed, ptr(out), ptr(A) if want_attn else None, st)
-            ctx.save_for_backward(query, key, value, pos, wqkv, g1, b1, g2, b2, keep_mask, qkv, A, *rstd)
+            ctx.save_for_backward(query, key, value, pos, flat, keep_mask, qkv, A, *rstd)
             ctx.cfg = cfg
             ctx.set_materialize_grads(False)
             ctx.mark_non_differentiable(A)
@@ -393,17 +430,18 @@ class _LinearAttentionFn(torch.autograd.Function):
         out = torch.empty((B, n, H * d), dtype=torch.float32, device=query.device)
         _launch("attn_xm", *xm_work, lib.gb200_attn_xm, dev, ops[0], ptr(pos), ptr(A), 0, B, H, n, dk, p,
                 ptr(out), H * d, 0, 1, 1.0, tc, st)
-        ctx.save_for_backward(query, key, value, pos, wqkv, g1, b1, g2, b2, keep_mask, qkv, A, *rstd)
+        ctx.save_for_backward(query, key, value, pos, flat, keep_mask, qkv, A, *rstd)
         ctx.cfg = cfg
         ctx.set_materialize_grads(False)
         return out, A
 
     @staticmethod
     def backward(ctx, dout, dA_ext):
-        (query, key, value, pos, wqkv, g1, b1, g2, b2, keep_mask, qkv, A, *rstd) = ctx.saved_tensors
+        (query, key, value, pos, flat, keep_mask, qkv, A, *rstd) = ctx.saved_tensors
         H, dk, p, eps, norm_on, scale, self_attn, mask_p, mask_seed, quadratic, want_attn = ctx.cfg
         lib = _lib.load()
         B, n, dm = query.shape
+        wqkv, _bq, g1, b1, g2, b2 = _unpack_attention_params(flat, dm, H, dk, norm_on is not None)
         T, d = B * n, dk + p
         dev, st = _dev(query), stream_of(query)
         tc = int(_PRECISION == "tf32")
@@ -422,7 +460,7 @@ class _LinearAttentionFn(torch.autograd.Function):
                     lib.gb200_fourier_quad_bwd, dev, ops[0], ops[1], ops[2], do_op, ptr(pos), B, H, n, dk, p, scale,
                     ptr(keep_mask), mask_p, mask_seed, ptr(dqkv), 3 * dm, 0, dm, 2 * dm, st)
             return _LinearAttentionFn._finish_backward(ctx, dqkv, blocks, rstd, qkv, g1, g2, query, key, value, wqkv,
-                                                       H, dk, T, dm, self_attn, dev, st)
+                                                       flat, H, dk, T, dm, self_attn, dev, st)
         # G = scale * mask2 * (Q~^T dO [+ external grad of A])
         G = torch.empty((B, H, d, d), dtype=torch.float32, device=query.device)
         xty_work = (2.0 * B * H * n * d * d, 4.0 * (T * dm + T * p + T * H * d))
@@ -452,17 +490,20 @@ class _LinearAttentionFn(torch.autograd.Function):
                 3 * dm, 2 * dm, 0, 1.0, tc, st)
         _launch("attn_xm", *xm_work, lib.gb200_attn_xm, dev, ops[2], ptr(pos), ptr(G), 1, B, H, n, dk, p, ptr(dqkv),
                 3 * dm, dm, 0, 1.0, tc, st)
-        return _LinearAttentionFn._finish_backward(ctx, dqkv, blocks, rstd, qkv, g1, g2, query, key, value, wqkv, H, dk,
-                                                   T, dm, self_attn, dev, st)
+        return _LinearAttentionFn._finish_backward(ctx, dqkv, blocks, rstd, qkv, g1, g2, query, key, value, wqkv, flat,
+                                                   H, dk, T, dm, self_attn, dev, st)
 
     @staticmethod
-    def _finish_backward(ctx, dqkv, blocks, rstd, qkv, g1, g2, query, key, value, wqkv, H, dk, T, dm, self_attn, dev,
-                         st):
-        """per-head LayerNorm backward on the normalised blocks, then the Q/K/V projection backward"""
+    def _finish_backward(ctx, dqkv, blocks, rstd, qkv, g1, g2, query, key, value, wqkv, flat, H, dk, T, dm, self_attn,
+                         dev, st):
+        """per-head LayerNorm backward on the normalised blocks, then the Q/K/V projection backward.  Every
+        parameter gradient is written straight into its slice of ONE flat buffer (the gradient of the packed
+        parameter vector), which _PackFn.backward hands out as views."""
         lib = _lib.load()
-        dgb = [None, None, None, None]
+        dflat = torch.empty_like(flat)
+        dwqkv, dbqkv, dg1, db1, dg2, db2 = _unpack_attention_params(dflat, dm, H, dk, bool(blocks))
         if blocks:
-            dgb = [torch.empty_like(g1), torch.empty_like(g1), torch.empty_like(g2), torch.empty_like(g2)]
+            dgb = [dg1, db1, dg2, db2]
             wsb = lib.gb200_headnorm_bwd_workspace_bytes(T, H, dk)
             w2 = workspace(wsb, qkv)
             _launch("headnorm_bwd", 28.0 * T * dm, 24.0 * T * dm, lib.gb200_headnorm_bwd, dev, ptr(dqkv), 3 * dm,
@@ -470,8 +511,6 @@ class _LinearAttentionFn(torch.autograd.Function):
                     ptr(rstd[1]), ptr(g1), ptr(g2), T, H, dk, ptr(dgb[0]), ptr(dgb[1]), ptr(dgb[2]), ptr(dgb[3]), 0,
                     ptr(w2), wsb, st)
         # projection backward
-        dwqkv = torch.empty_like(wqkv)
-        dbqkv = torch.empty(3 * dm, dtype=torch.float32, device=query.device)
         colsum(dqkv, T, 3 * dm, 3 * dm, dbqkv)
         xs = [t.reshape(T, dm) for t in (query, key, value)]
         dq = dk_ = dv = None
@@ -491,10 +530,22 @@ class _LinearAttentionFn(torch.autograd.Function):
                     gemm(dqkv, wqkv, gi, T, dm, dm, lda=3 * dm, ldb=dm, ldc=dm, a_off=i * dm, b_off=i * dm * dm)
                 grads.append(gi)
             dq, dk_, dv = grads
-        return (dq, dk_, dv, None, dwqkv, dbqkv, dgb[0], dgb[1], dgb[2], dgb[3], None, None)
+        return (dq, dk_, dv, None, dflat, None, None)
 
 
-def linear_attention(query, key, value, pos, wqkv, bqkv, norm_params, keep_mask, *, n_head, pos_dim,
+def _unpack_attention_params(flat, dm, H, dk, has_norm):
+    """views of the packed [W_qkv (3dm,dm) | b_qkv (3dm) | gamma1 | beta1 | gamma2 | beta2 (H,dk each)] vector"""
+    o = 3 * dm * dm
+    wqkv = flat[:o].view(3 * dm, dm)
+    bqkv = flat[o:o + 3 * dm]
+    o += 3 * dm
+    if not has_norm:
+        return wqkv, bqkv, None, None, None, None
+    tabs = [flat[o + i * dm:o + (i + 1) * dm].view(H, dk) for i in range(4)]
+    return (wqkv, bqkv, *tabs)
+
+
+def linear_attention(query, key, value, pos, flat, has_norm, keep_mask, *, n_head, pos_dim,
                      eps, attention_type, self_attn, mask_p=0.0, quadratic=False, want_attn=False):
     """keep_mask: explicit (B,H,d,d) uint8 keep-mask, or None with mask_p > 0 for the in-kernel Philox
     dropout of the attention matrix (no mask tensor, regenerated in backward)."""
@@ -503,18 +554,15 @@ def linear_attention(query, key, value, pos, wqkv, bqkv, norm_params, keep_mask,
     p = pos_dim if pos is not None else 0
     d = dk + p
     if attention_type == "galerkin":
-        norm_on, scale = ("kv" if norm_params is not None else None), 1.0 / n
+        norm_on, scale = ("kv" if has_norm else None), 1.0 / n
     else:
-        norm_on, scale = ("qk" if norm_params is not None else None), 1.0 / (math.sqrt(d) * n)
-    g1 = b1 = g2 = b2 = None
-    if norm_params is not None:
-        g1, b1, g2, b2 = norm_params
+        norm_on, scale = ("qk" if has_norm else None), 1.0 / (math.sqrt(d) * n)
     mask_p = 0.0 if keep_mask is not None else float(mask_p)
     cfg = (n_head, dk, p, float(eps), norm_on, float(scale), bool(self_attn), mask_p,
            next_seed() if mask_p > 0.0 else 0, bool(quadratic), bool(want_attn))
     pos_c = None if pos is None else pos.contiguous()
-    return _LinearAttentionFn.apply(query.contiguous(), key.contiguous(), value.contiguous(), pos_c, wqkv, bqkv,
-                                    g1, b1, g2, b2, keep_mask, cfg)
+    return _LinearAttentionFn.apply(query.contiguous(), key.contiguous(), value.contiguous(), pos_c, flat, keep_mask,
+                                    cfg)
 
 
 # ------------------------------------------------------------------------------------------

@@ -99,15 +99,6 @@ class SimpleAttention(nn.Module):
         """Explicit keep-mask (B,H,d,d), 1 = keep, used instead of a random draw on the next forward."""
         self._next_mask = mask
 
-    def _norm_params(self):
-        if not self.add_norm:
-            return None
-        second = self.norm_V if self.attention_type in _GALERKIN else self.norm_Q
-        return (torch.stack([m.weight for m in self.norm_K]).contiguous(),
-                torch.stack([m.bias for m in self.norm_K]).contiguous(),
-                torch.stack([m.weight for m in second]).contiguous(),
-                torch.stack([m.bias for m in second]).contiguous())
-
     def forward(self, query, key, value, pos=None, mask=None, weight=None):
         x, attn_weight = self.forward_heads(query, key, value, pos=pos, mask=mask, weight=weight)
         if pos is not None and self.pos_dim > 0:
@@ -130,8 +121,14 @@ class SimpleAttention(nn.Module):
         p = self.pos_dim if use_pos else 0
         d = self.d_k + p
         self_attn = (query is key) and (key is value)
-        wqkv = torch.cat([lin.weight for lin in self.linears], dim=0)
-        bqkv = torch.cat([lin.bias for lin in self.linears], dim=0)
+        # W_qkv (3 d_model, d_model), b_qkv and the per-head LayerNorm tables, assembled by one pack launch
+        dm = self.n_head * self.d_k
+        parts = [lin.weight for lin in self.linears] + [lin.bias for lin in self.linears]
+        if self.add_norm:
+            second = self.norm_V if self.attention_type in _GALERKIN else self.norm_Q
+            for mods, attr in ((self.norm_K, "weight"), (self.norm_K, "bias"), (second, "weight"), (second, "bias")):
+                parts += [getattr(m, attr) for m in mods]
+        flat = GF.pack(parts)     # [W_qkv | b_qkv | gamma_1 | beta_1 | gamma_2 | beta_2]; its gradient comes back flat too
 
         keep = self._next_mask
         self._next_mask = None
@@ -147,8 +144,8 @@ class SimpleAttention(nn.Module):
         # linear-form kernels are used; with the n x n dropout the quadratic flash-style kernels run instead.
         quadratic = fourier and (keep is not None or mask_p > 0.0 or self.materialize_attn)
 
-        x, attn = GF.linear_attention(query, key, value, pos if use_pos else None, wqkv, bqkv,
-                                      self._norm_params(), keep, n_head=self.n_head, pos_dim=p,
+        x, attn = GF.linear_attention(query, key, value, pos if use_pos else None, flat, bool(self.add_norm),
+                                      keep, n_head=self.n_head, pos_dim=p,
                                       eps=self.eps, attention_type='fourier' if fourier else 'galerkin',
                                       self_attn=self_attn, mask_p=mask_p, quadratic=quadratic,
                                       want_attn=self.materialize_attn)

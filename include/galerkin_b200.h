@@ -43,6 +43,11 @@ unsigned long long gb200_launch_count(void);
  * masks while forward and backward of one step still agree.  NULL (default) disables the offset. */
 int gb200_set_rng_offset_ptr(const unsigned long long* device_counter);
 
+/* dst = concat(srcs[0..n)) in one launch (n <= 64; srcs / sizes are HOST arrays of device pointers / element counts).
+ * Assembles W_qkv, b_qkv and the per-head LayerNorm tables from the reference's separate parameters
+ * (libs/layers.py:810-811, 945-946) without torch.cat / torch.stack kernels. */
+int gb200_pack(int device, float* dst, const float* const* srcs, const long long* sizes, int n, void* stream);
+
 /* ------------------------------------------------------------------ dense layers ------------
  * C[b] = R[b] + rscale * dropout_p( act( alpha * op(A[b]) . op(B[b]) + bias ) )   (+= C if accumulate)
  *   op(A): transA ? A stored [K,M] : A stored [M,K];  op(B): transB ? B stored [N,K] : B stored [K,N]
