@@ -249,7 +249,9 @@ def main():
                           + args.attn_dropout,
                   l2="256 MiB buffer written between timed steps (L2 flush)",
                   launch="eager" if args.no_graph else "whole fwd+bwd step replayed from one CUDA graph",
-                  gemm_precision=args.precision)
+                  gemm_precision=args.precision,
+                  backward_streams="dW / db launches on 2 side streams (parallel graph branches)"
+                  if os.environ.get("GB200_BWD_STREAMS", "1") != "0" else "off")
 
     if args.impl == "reference":
         if rank != 0:
@@ -389,6 +391,8 @@ def main():
         peaks = measured_peaks()
         prof_steps = min(args.steps, 5)
         GF.Profiler.reset()
+        streams_on = GF._BWD_STREAMS
+        GF.set_backward_streams(False)      # serial launches: each event pair then brackets exactly one kernel
         step_ms_prof = 0.0
         for _ in range(prof_steps):
             # Eager launches, but queued behind a ~30 ms spin kernel so the GPU never waits for the host:
@@ -405,6 +409,7 @@ def main():
             GF.Profiler.enabled = False
             torch.cuda.synchronize()
             step_ms_prof += tot0.elapsed_time(tot1) / prof_steps
+        GF.set_backward_streams(streams_on)
         if graphed is not None:
             for p_, g_ in zip(graphed.params, graphed.static_grads):
                 p_.grad = g_

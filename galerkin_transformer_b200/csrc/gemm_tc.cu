@@ -107,7 +107,17 @@ struct TcArgs {
     float* ws;
     int vec4;             // C/R/Z/ws rows are 16-byte aligned and N % 4 == 0: float4 epilogue
     int truncate;         // 1: skip the round-to-nearest pass (operands truncated to TF32 by the tensor core)
+    unsigned long long* trace;   // diagnostics: 8 globaltimer stamps per CTA (gb200_gemm_tc_set_trace), else null
 };
+
+__device__ __forceinline__ void tc_stamp(const TcArgs& g, int slot) {
+    if (g.trace) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        const long long cta = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        g.trace[cta * 8 + slot] = t;
+    }
+}
 
 // activation with fast intrinsics (the TF32 path is not bit-exact fp32 anyway)
 template <int ACT>
@@ -219,6 +229,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     const int kbeg = split * g.kchunk;
     const int kend = min(g.K, kbeg + g.kchunk);
     const int nkb = (kend - kbeg + TC_BK - 1) / TC_BK;
+    if (threadIdx.x == 64) tc_stamp(g, 0);                                   // CTA entry
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
@@ -241,6 +252,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 64) tc_stamp(g, 1);                                   // barriers + TMEM ready
 
     if (warp == 0) {
         if (lane == 0) {   // ---------------- TMA producer ----------------
@@ -308,6 +320,8 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
                 const int s = kb % TC_STAGES;
                 const uint32_t ph = (kb / TC_STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
+                if (ct == 0 && kb == 0) tc_stamp(g, 2);                      // first tile landed
+                if (ct == 0 && kb == nkb - 1) tc_stamp(g, 3);                // last tile landed
                 float4* tile = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
 #pragma unroll 4
                 for (int i = ct; i < STAGE_BYTES / 16; i += 128) {
@@ -326,6 +340,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
                 if (lane == 0)
                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&conv_bar[s])) : "memory");
             }
+            if (ct == 0) tc_stamp(g, 4);                                     // last tile rounded
         }
         const int q = warp % 4;                  // TMEM lane quarter this warp may access
         constexpr int DS = BN + 4;               // row pitch = 1 (mod 8) float4s: conflict-free float4 stores (thread = row)
@@ -335,6 +350,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
             mbar_wait(tmem_full, 0);
             tc_fence_after();
         }
+        if (threadIdx.x == 64) tc_stamp(g, 5);                               // accumulator complete
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t v[32];
@@ -364,6 +380,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
         }
         tc_fence_before();
         __syncwarp();
+        if (threadIdx.x == 64) tc_stamp(g, 6);                               // TMEM drained to shared memory
         const int ncols = min(BN, g.N - n0);
         const GemmEpilogue& ep = g.ep;
         const unsigned long long seed = ep.seed + ((ep.drop_p > 0.f && ep.seed_off) ? *ep.seed_off : 0ull);
@@ -426,6 +443,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
         }
     }
     __syncthreads();
+    if (threadIdx.x == 64) tc_stamp(g, 7);                                   // all epilogue stores issued
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
@@ -768,6 +786,12 @@ extern "C" int gb200_gemm_tc_suggest_ksplit(int M, int N, int K) {
 
 namespace gb200 {
 struct HeadNormFusion { int dk, lo, hi, heads; float eps; float* rstd[2]; };
+static unsigned long long* g_tc_trace = nullptr;
+extern "C" int gb200_gemm_tc_set_trace(unsigned long long* device_buffer) {
+    g_tc_trace = device_buffer;
+    return 0;
+}
+
 static thread_local HeadNormFusion g_hn = {0, 0, 0, 0, 0.f, {nullptr, nullptr}};
 }
 
@@ -789,7 +813,7 @@ extern "C" int gb200_gemm_tc(int device, const float* A, int lda, int transA, co
     const int bn = pick_bn(M, N);
     TcArgs g;
     g.ep.C = C; g.ep.ldc = ldc; g.ep.sC = 0; g.ep.alpha = alpha; g.ep.bias = bias; g.ep.act = act; g.ep.Z = Zout;
-    g.ep.ldz = ldz; g.ep.drop_p = drop_p; g.ep.seed = seed; g.ep.seed_off = rng_offset_ptr(); g.ep.R = R; g.ep.ldr = ldr; g.ep.rscale = rscale;
+    g.ep.ldz = ldz; g.ep.drop_p = drop_p; g.ep.seed = seed; g.ep.seed_off = rng_offset_ptr(); g.trace = g_tc_trace; g.ep.R = R; g.ep.ldr = ldr; g.ep.rscale = rscale;
     g.ep.accumulate = accumulate;
     g.ep.hn_dk = g_hn.dk; g.ep.hn_lo = g_hn.lo; g.ep.hn_hi = g_hn.hi; g.ep.hn_heads = g_hn.heads; g.ep.hn_eps = g_hn.eps;
     g.ep.hn_rstd[0] = g_hn.rstd[0]; g.ep.hn_rstd[1] = g_hn.rstd[1];

@@ -5,6 +5,8 @@ libgalerkin_b200.so; PyTorch is used for memory (torch.empty from the caching al
 streams and the autograd graph only.  Backward runs on PyTorch's autograd thread; the
 library is re-entrant and takes the device ordinal on every call.
 """
+import contextlib
+import os
 import math
 import threading
 
@@ -104,6 +106,51 @@ def _launch(family, flops, nbytes, fn, *args):
         rc = fn(*args)
     if rc != 0:
         check(rc, family)
+
+
+# ------------------------------------------------------------------------------------------
+# backward fork/join: weight- and bias-gradient launches leave the critical path
+# ------------------------------------------------------------------------------------------
+_BWD_STREAMS = os.environ.get("GB200_BWD_STREAMS", "1") != "0"
+_side_streams = {}
+
+
+def set_backward_streams(on):
+    """Run the parameter-gradient launches of each backward (dW GEMM + split-K reduce, bias column sums) on side
+    streams, concurrently with the input-gradient GEMM that the next backward node is waiting for.  Every one of
+    these kernels is a single latency-bound wave at the shipped sizes, so they overlap almost freely; inside a
+    captured step the fork/join becomes parallel branches of the CUDA graph."""
+    global _BWD_STREAMS
+    _BWD_STREAMS = bool(on)
+
+
+class _Fork:
+    """`with fork.side(i):` enqueues on side stream i (which first waits for everything enqueued on the launching
+    stream so far); `join()` makes the launching stream wait for the side work.  Outputs must be allocated BEFORE
+    entering a side context (they then belong to the launching stream's allocator pool, and the join orders every
+    later use after the side-stream writes); scratch allocated inside stays on the side stream."""
+
+    def __init__(self, like):
+        self.device = like.device
+        self.main = torch.cuda.current_stream(self.device)
+        self.used = []
+
+    def side(self, i):
+        if not _BWD_STREAMS:
+            return contextlib.nullcontext()
+        pool = _side_streams.setdefault(self.device.index, [])
+        while len(pool) <= i:
+            pool.append(torch.cuda.Stream(device=self.device))
+        s = pool[i]
+        if s not in self.used:
+            s.wait_stream(self.main)
+            self.used.append(s)
+        return torch.cuda.stream(s)
+
+    def join(self):
+        for s in self.used:
+            self.main.wait_stream(s)
+        self.used = []
 
 
 # ------------------------------------------------------------------------------------------
@@ -234,15 +281,19 @@ class _LinearFn(torch.autograd.Function):
                 g = epilogue_bwd(dy, M, N, z=z, y=y, act=act, rscale=rscale, drop_p=drop_p, seed=seed)
         else:
             g = dy
+        fork = _Fork(g)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(weight)
+            with fork.side(0):
+                gemm(g, x, dw, N, K, M, lda=N, ldb=K, ldc=K, transA=True)
+        if want_db:
+            db = torch.empty(N, dtype=torch.float32, device=x.device)
+            with fork.side(1):
+                colsum(g, M, N, N, db)
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             gemm(g, weight, dx, M, K, N, lda=N, ldb=K, ldc=K)
-        if ctx.needs_input_grad[1]:
-            dw = torch.empty_like(weight)
-            gemm(g, x, dw, N, K, M, lda=N, ldb=K, ldc=K, transA=True)
-        if want_db:
-            db = torch.empty(N, dtype=torch.float32, device=x.device)
-            colsum(g, M, N, N, db)
+        fork.join()
         dres = dy if (has_res and ctx.needs_input_grad[3]) else None
         return dx, dw, db, dres, None, None, None, None
 
@@ -286,22 +337,27 @@ class _LinearCatFn(torch.autograd.Function):
         M, K1 = x1.shape
         K2 = x2.shape[1]
         N = w1.shape[0]
-        dx1 = dx2 = dw = db = None
+        dx1 = dx2 = dw = db = dw1 = dw2 = None
+        fork = _Fork(dy)
+        if ctx.needs_input_grad[2]:
+            dw1 = torch.empty_like(w1)
+            dw2 = torch.empty_like(w2)
+            with fork.side(0):
+                gemm(dy, x1, dw1, N, K1, M, lda=N, ldb=K1, ldc=K1, transA=True)
+                gemm(dy, x2, dw2, N, K2, M, lda=N, ldb=K2, ldc=K2, transA=True)
+        if ctx.has_bias and ctx.needs_input_grad[3]:
+            db = torch.empty(N, dtype=torch.float32, device=dy.device)
+            with fork.side(1):
+                colsum(dy, M, N, N, db)
         if ctx.needs_input_grad[0]:
             dx1 = torch.empty_like(x1)
             gemm(dy, w1, dx1, M, K1, N, lda=N, ldb=K1, ldc=K1)
         if ctx.needs_input_grad[1]:
             dx2 = torch.empty_like(x2)
             gemm(dy, w2, dx2, M, K2, N, lda=N, ldb=K2, ldc=K2)
-        if ctx.needs_input_grad[2]:
-            dw1 = torch.empty_like(w1)
-            dw2 = torch.empty_like(w2)
-            gemm(dy, x1, dw1, N, K1, M, lda=N, ldb=K1, ldc=K1, transA=True)
-            gemm(dy, x2, dw2, N, K2, M, lda=N, ldb=K2, ldc=K2, transA=True)
+        fork.join()
+        if dw1 is not None:
             dw = torch.cat([dw1, dw2], dim=1)
-        if ctx.has_bias and ctx.needs_input_grad[3]:
-            db = torch.empty(N, dtype=torch.float32, device=dy.device)
-            colsum(dy, M, N, N, db)
         return dx1, dx2, dw, db
 
 
@@ -510,26 +566,32 @@ class _LinearAttentionFn(torch.autograd.Function):
                     blocks[0] * dm, blocks[1] * dm, ptr(qkv), 3 * dm, blocks[0] * dm, blocks[1] * dm, ptr(rstd[0]),
                     ptr(rstd[1]), ptr(g1), ptr(g2), T, H, dk, ptr(dgb[0]), ptr(dgb[1]), ptr(dgb[2]), ptr(dgb[3]), 0,
                     ptr(w2), wsb, st)
-        # projection backward
-        colsum(dqkv, T, 3 * dm, 3 * dm, dbqkv)
+        # projection backward: weight and bias gradients on side streams, input gradients on the launching one
+        fork = _Fork(dqkv)
+        with fork.side(1):
+            colsum(dqkv, T, 3 * dm, 3 * dm, dbqkv)
         xs = [t.reshape(T, dm) for t in (query, key, value)]
         dq = dk_ = dv = None
         if self_attn:
-            gemm(dqkv, xs[0], dwqkv, 3 * dm, dm, T, lda=3 * dm, ldb=dm, ldc=dm, transA=True)
+            with fork.side(0):
+                gemm(dqkv, xs[0], dwqkv, 3 * dm, dm, T, lda=3 * dm, ldb=dm, ldc=dm, transA=True)
             if ctx.needs_input_grad[0]:
                 dq = torch.empty_like(query)
                 gemm(dqkv, wqkv, dq, T, dm, 3 * dm, lda=3 * dm, ldb=dm, ldc=dm)
         else:
+            with fork.side(0):
+                for i in range(3):
+                    gemm(dqkv, xs[i], dwqkv, dm, dm, T, lda=3 * dm, ldb=dm, ldc=dm, transA=True, a_off=i * dm,
+                         c_off=i * dm * dm)
             grads = []
             for i in range(3):
-                gemm(dqkv, xs[i], dwqkv, dm, dm, T, lda=3 * dm, ldb=dm, ldc=dm, transA=True, a_off=i * dm,
-                     c_off=i * dm * dm)
                 gi = None
                 if ctx.needs_input_grad[i]:
                     gi = torch.empty_like(query)
                     gemm(dqkv, wqkv, gi, T, dm, dm, lda=3 * dm, ldb=dm, ldc=dm, a_off=i * dm, b_off=i * dm * dm)
                 grads.append(gi)
             dq, dk_, dv = grads
+        fork.join()
         return (dq, dk_, dv, None, dflat, None, None)
 
 

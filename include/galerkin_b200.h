@@ -73,6 +73,10 @@ int gb200_gemm(int device, const float* A, int lda, int transA, const float* B, 
  * gb200_gemm.  Relative error ~4e-4 per contraction (TF32), see DESIGN.md. */
 int gb200_gemm_tc_supported(const float* A, int lda, const float* B, int ldb, int M, int N, int K);
 int gb200_gemm_tc_suggest_ksplit(int M, int N, int K);
+/* Diagnostics: when `device_buffer` is non-null every CTA of subsequent gb200_gemm_tc launches writes eight
+ * %globaltimer stamps (entry, setup done, first/last tile landed, last tile rounded, accumulator complete,
+ * TMEM drained, stores issued) to device_buffer[8 * linear_cta + slot].  Null (default) disables it. */
+int gb200_gemm_tc_set_trace(unsigned long long* device_buffer);
 int gb200_gemm_tc(int device, const float* A, int lda, int transA, const float* B, int ldb, int transB,
                   float* C, int ldc, int M, int N, int K, float alpha, const float* bias, int act,
                   float* Zout, int ldz, float drop_p, unsigned long long seed, const float* R, int ldr,
