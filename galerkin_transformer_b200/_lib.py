@@ -11,7 +11,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libgalerkin_b200.so")
+LIB_PATH = os.environ.get("GB200_LIB", os.path.join(_HERE, "csrc", "libgalerkin_b200.so"))   # override: tuning builds
 
 _lock = threading.Lock()
 _lib = None

@@ -5,7 +5,7 @@ import subprocess
 import sys
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
-OUT = os.path.join(CSRC, "libgalerkin_b200.so")
+OUT = os.environ.get("GB200_LIB", os.path.join(CSRC, "libgalerkin_b200.so"))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -27,7 +27,8 @@ def build(force=False, verbose=False):
     if not force and not is_stale():
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + sources()
+    extra = os.environ.get("GB200_NVCC_EXTRA", "").split()      # tuning experiments: e.g. -DGB200_PDL_MODE=0
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

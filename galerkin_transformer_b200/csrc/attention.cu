@@ -29,6 +29,7 @@ constexpr int HN_ROWS = 32;
 
 __global__ void headnorm_fwd_kernel(float* __restrict__ x, int ld, int col0, long long T, int H, int dk,
                                     float eps, float* __restrict__ rstd_out) {
+    pdl_enter();
     extern __shared__ float sm[];
     const int W = H * dk, WS = W + 1;
     const long long t0 = (long long)blockIdx.x * HN_ROWS;
@@ -64,6 +65,7 @@ __global__ void headnorm_bwd_kernel(float* __restrict__ dy, int lddy, int dcol0,
                                     const float* __restrict__ xhat, int ldx, int xcol0,
                                     const float* __restrict__ rstd, const float* __restrict__ gamma,
                                     long long T, int H, int dk, float* __restrict__ part) {
+    pdl_enter();
     extern __shared__ float sm[];
     const int W = H * dk, WS = W + 1;
     float* sdy = sm;
@@ -133,6 +135,7 @@ __device__ __forceinline__ float group_sum(float v) {
 template <int LG>
 __global__ void __launch_bounds__(256) headnorm_fwd_vec_kernel(float* __restrict__ x, int ld, HeadNormBlocks blk,
                                                                long long T, int H, int dk, float eps) {
+    pdl_enter();
     const int col0 = blk.col0[blockIdx.y];
     float* rstd_out = blk.rstd[blockIdx.y];
     const int rowq = H * LG;                              // float4s per row
@@ -161,6 +164,7 @@ template <int LG>
 __global__ void __launch_bounds__(256) headnorm_bwd_vec_kernel(float* __restrict__ dy, int lddy,
                                                                const float* __restrict__ xhat, int ldx,
                                                                HeadNormBlocks blk, long long T, int H, int dk) {
+    pdl_enter();
     __shared__ float4 sg[256], sb[256];
     const int bi = blockIdx.y;
     const int rowq = H * LG;
@@ -219,6 +223,7 @@ constexpr int HN_VEC_BLOCKS = 296;
 __global__ void headnorm_bwd_reduce_kernel(const float* __restrict__ part, int nblocks, int W,
                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
                                            int accumulate) {
+    pdl_enter();
     // blockIdx.y = 0: dgamma, 1: dbeta
     reduce_partials_2d(part + (long long)blockIdx.y * W, nblocks, 2LL * W, W, 1.f, accumulate,
                        blockIdx.y == 0 ? dgamma : dbeta);
@@ -233,6 +238,7 @@ template <int DP>
 __global__ void __launch_bounds__(256) xty_kernel(HeadOperand L, HeadOperand R, const float* __restrict__ pos,
                                                   int p, int dk, int H, int n, int nsplit, int chunk,
                                                   float* __restrict__ part) {
+    pdl_enter();
     constexpr int TC = 32, MT = DP / 16;
     __shared__ float Ls[TC][DP + 1];
     __shared__ float Rs[TC][DP + 1];
@@ -290,6 +296,7 @@ __global__ void xty_reduce_kernel(const float* __restrict__ part, int nsplit, in
                                   float scale, const unsigned char* __restrict__ mask, float mask_p,
                                   unsigned long long mask_seed, const unsigned long long* seed_off,
                                   float* __restrict__ out) {
+    pdl_enter();
     if (mask_p > 0.f && seed_off) mask_seed += *seed_off;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x) {
@@ -316,6 +323,7 @@ __global__ void __launch_bounds__(256) xm_kernel(HeadOperand L, const float* __r
                                                  const float* __restrict__ Mat, int transM, int p, int dk,
                                                  int H, int n, float* __restrict__ out, int ldo, int ocol0,
                                                  int out_augmented, float oscale) {
+    pdl_enter();
     constexpr int TT = 64, MT = DP / 16;
     extern __shared__ float sm[];
     float* Ms = sm;                    // [DP][DP+1]   Ms[i][j]
@@ -396,7 +404,7 @@ extern "C" int gb200_headnorm_fwd(int device, float* x, int ld, int col0, int co
         int blocks = cdiv(T, rpb);
         if (blocks > HN_VEC_BLOCKS) blocks = HN_VEC_BLOCKS;
         dim3 grid(blocks, nblk);
-#define HN_FWD(LG) headnorm_fwd_vec_kernel<LG><<<grid, 256, 0, st>>>(x, ld, blk, T, H, dk, eps)
+#define HN_FWD(LG) launch_pdl(headnorm_fwd_vec_kernel<LG>, grid, 256, 0, st, x, ld, blk, T, H, dk, eps)
         switch (lg) { case 1: HN_FWD(1); break; case 2: HN_FWD(2); break; case 4: HN_FWD(4); break;
                       case 8: HN_FWD(8); break; case 16: HN_FWD(16); break; default: HN_FWD(32); }
 #undef HN_FWD
@@ -406,8 +414,8 @@ extern "C" int gb200_headnorm_fwd(int device, float* x, int ld, int col0, int co
     GB_REQUIRE(smem <= 200 * 1024, "gb200_headnorm_fwd: H*d_k=%d too wide", H * dk);
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(headnorm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    headnorm_fwd_kernel<<<cdiv(T, HN_ROWS), 256, smem, st>>>(x, ld, col0, T, H, dk, eps, rstd);
-    if (nblk == 2) headnorm_fwd_kernel<<<cdiv(T, HN_ROWS), 256, smem, st>>>(x, ld, col0b, T, H, dk, eps, rstd_b);
+    launch_pdl(headnorm_fwd_kernel, cdiv(T, HN_ROWS), 256, smem, st, x, ld, col0, T, H, dk, eps, rstd);
+    if (nblk == 2) launch_pdl(headnorm_fwd_kernel, cdiv(T, HN_ROWS), 256, smem, st, x, ld, col0b, T, H, dk, eps, rstd_b);
     return check_launch("gb200_headnorm_fwd", nblk);
 }
 
@@ -448,14 +456,14 @@ extern "C" int gb200_headnorm_bwd(int device, float* dy, int lddy, int dcol0, in
         blk.rstd[0] = const_cast<float*>(rstd); blk.rstd[1] = const_cast<float*>(rstd_b);
         blk.gamma[0] = gamma; blk.gamma[1] = gamma_b; blk.part[0] = part_a; blk.part[1] = part_b;
         dim3 grid(blocks, nblk);
-#define HN_BWD(LG) headnorm_bwd_vec_kernel<LG><<<grid, 256, 0, st>>>(dy, lddy, xhat, ldx, blk, T, H, dk)
+#define HN_BWD(LG) launch_pdl(headnorm_bwd_vec_kernel<LG>, grid, 256, 0, st, dy, lddy, xhat, ldx, blk, T, H, dk)
         switch (lg) { case 1: HN_BWD(1); break; case 2: HN_BWD(2); break; case 4: HN_BWD(4); break;
                       case 8: HN_BWD(8); break; case 16: HN_BWD(16); break; default: HN_BWD(32); }
 #undef HN_BWD
-        headnorm_bwd_reduce_kernel<<<dim3(cdiv(W, 32), 2), dim3(32, 32), 0, st>>>(part_a, blocks, W, dgamma, dbeta,
+        launch_pdl(headnorm_bwd_reduce_kernel, dim3(cdiv(W, 32), 2), dim3(32, 32), 0, st, part_a, blocks, W, dgamma, dbeta,
                                                                                 accumulate);
         if (nblk == 2)
-            headnorm_bwd_reduce_kernel<<<dim3(cdiv(W, 32), 2), dim3(32, 32), 0, st>>>(part_b, blocks, W, dgamma_b,
+            launch_pdl(headnorm_bwd_reduce_kernel, dim3(cdiv(W, 32), 2), dim3(32, 32), 0, st, part_b, blocks, W, dgamma_b,
                                                                                     dbeta_b, accumulate);
         return check_launch("gb200_headnorm_bwd", 1 + nblk);
     }
@@ -465,13 +473,13 @@ extern "C" int gb200_headnorm_bwd(int device, float* dy, int lddy, int dcol0, in
         cudaFuncSetAttribute(headnorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int nblocks = cdiv(T, HN_ROWS);
     float* part_b = workspace + (size_t)nblocks * 2 * W;
-    headnorm_bwd_kernel<<<nblocks, 256, smem, st>>>(dy, lddy, dcol0, xhat, ldx, xcol0, rstd, gamma, T, H, dk, part_a);
-    headnorm_bwd_reduce_kernel<<<dim3(cdiv(W, 32), 2), dim3(32, 32), 0, st>>>(part_a, nblocks, W, dgamma, dbeta,
+    launch_pdl(headnorm_bwd_kernel, nblocks, 256, smem, st, dy, lddy, dcol0, xhat, ldx, xcol0, rstd, gamma, T, H, dk, part_a);
+    launch_pdl(headnorm_bwd_reduce_kernel, dim3(cdiv(W, 32), 2), dim3(32, 32), 0, st, part_a, nblocks, W, dgamma, dbeta,
                                                                             accumulate);
     if (nblk == 2) {
-        headnorm_bwd_kernel<<<nblocks, 256, smem, st>>>(dy, lddy, dcol0b, xhat, ldx, xcol0b, rstd_b, gamma_b, T, H, dk,
+        launch_pdl(headnorm_bwd_kernel, nblocks, 256, smem, st, dy, lddy, dcol0b, xhat, ldx, xcol0b, rstd_b, gamma_b, T, H, dk,
                                                         part_b);
-        headnorm_bwd_reduce_kernel<<<dim3(cdiv(W, 32), 2), dim3(32, 32), 0, st>>>(part_b, nblocks, W, dgamma_b,
+        launch_pdl(headnorm_bwd_reduce_kernel, dim3(cdiv(W, 32), 2), dim3(32, 32), 0, st, part_b, nblocks, W, dgamma_b,
                                                                                 dbeta_b, accumulate);
     }
     return check_launch("gb200_headnorm_bwd", 2 * nblk);
@@ -510,19 +518,19 @@ extern "C" int gb200_attn_xty(int device, const gb200_head_operand* L, const gb2
     cudaStream_t st = as_stream(stream);
     HeadOperand l = make_op(L), r = make_op(R);
     if (tensor_cores && d <= 64) {       // warp-level TF32 MMA, tiles right-sized to d
-        if (d <= 24) xty_mma_kernel<2, 3><<<grid, 256, 0, st>>>(l, r, pos, p, dk, H, n, nsplit, chunk, workspace);
-        else if (d <= 40) xty_mma_kernel<3, 5><<<grid, 256, 0, st>>>(l, r, pos, p, dk, H, n, nsplit, chunk, workspace);
-        else if (d <= 56) xty_mma_kernel<4, 7><<<grid, 256, 0, st>>>(l, r, pos, p, dk, H, n, nsplit, chunk, workspace);
-        else xty_mma_kernel<4, 8><<<grid, 256, 0, st>>>(l, r, pos, p, dk, H, n, nsplit, chunk, workspace);
+        if (d <= 24) launch_pdl(xty_mma_kernel<2, 3>, grid, 256, 0, st, l, r, pos, p, dk, H, n, nsplit, chunk, workspace);
+        else if (d <= 40) launch_pdl(xty_mma_kernel<3, 5>, grid, 256, 0, st, l, r, pos, p, dk, H, n, nsplit, chunk, workspace);
+        else if (d <= 56) launch_pdl(xty_mma_kernel<4, 7>, grid, 256, 0, st, l, r, pos, p, dk, H, n, nsplit, chunk, workspace);
+        else launch_pdl(xty_mma_kernel<4, 8>, grid, 256, 0, st, l, r, pos, p, dk, H, n, nsplit, chunk, workspace);
     } else
-    if (dp == 32) xty_kernel<32><<<grid, 256, 0, st>>>(l, r, pos, p, dk, H, n, nsplit, chunk, workspace);
-    else if (dp == 64) xty_kernel<64><<<grid, 256, 0, st>>>(l, r, pos, p, dk, H, n, nsplit, chunk, workspace);
-    else xty_kernel<128><<<grid, 256, 0, st>>>(l, r, pos, p, dk, H, n, nsplit, chunk, workspace);
+    if (dp == 32) launch_pdl(xty_kernel<32>, grid, 256, 0, st, l, r, pos, p, dk, H, n, nsplit, chunk, workspace);
+    else if (dp == 64) launch_pdl(xty_kernel<64>, grid, 256, 0, st, l, r, pos, p, dk, H, n, nsplit, chunk, workspace);
+    else launch_pdl(xty_kernel<128>, grid, 256, 0, st, l, r, pos, p, dk, H, n, nsplit, chunk, workspace);
     long long total = (long long)B * H * d * d;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     GB_REQUIRE(mask_p >= 0.f && mask_p < 1.f, "gb200_attn_xty: mask_p=%f outside [0,1)", mask_p);
-    xty_reduce_kernel<<<blocks, 256, 0, st>>>(workspace, nsplit, d * d, total, scale, keep_mask, mask_p, mask_seed,
+    launch_pdl(xty_reduce_kernel, blocks, 256, 0, st, workspace, nsplit, d * d, total, scale, keep_mask, mask_p, mask_seed,
                                               rng_offset_ptr(), out);
     return check_launch("gb200_attn_xty", 2);
 }
@@ -530,6 +538,7 @@ extern "C" int gb200_attn_xty(int device, const gb200_head_operand* L, const gb2
 // scale tensor of the in-kernel attention dropout: out[e] = 0 or 1/(1-p), same stream as gb200_attn_xty
 __global__ void philox_scale_kernel(float* __restrict__ out, long long total, float p, unsigned long long seed,
                                     const unsigned long long* seed_off) {
+    pdl_enter();
     if (seed_off) seed += *seed_off;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x)
@@ -543,7 +552,7 @@ extern "C" int gb200_philox_scale(int device, float* out, long long total, float
     if (total == 0) return GB200_OK;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    philox_scale_kernel<<<blocks, 256, 0, as_stream(stream)>>>(out, total, p, seed, rng_offset_ptr());
+    launch_pdl(philox_scale_kernel, blocks, 256, 0, as_stream(stream), out, total, p, seed, rng_offset_ptr());
     return check_launch("gb200_philox_scale");
 }
 
@@ -562,7 +571,7 @@ extern "C" int gb200_attn_xm(int device, const gb200_head_operand* L, const floa
     HeadOperand l = make_op(L);
     if (tensor_cores && d <= 64) {
 #define LAUNCH_XMM(KT, NT, TT)                                                                               \
-    xm_mma_kernel<KT, NT, TT><<<dim3(cdiv(n, TT), B * H), TT * 2, 0, st>>>(l, pos, M, transM, p, dk, H, n, out, ldo, \
+    launch_pdl(xm_mma_kernel<KT, NT, TT>, dim3(cdiv(n, TT), B * H), TT * 2, 0, st, l, pos, M, transM, p, dk, H, n, out, ldo, \
                                                                            ocol0, out_augmented, out_scale)
         if (d <= 24) LAUNCH_XMM(3, 3, 128);
         else if (d <= 40) LAUNCH_XMM(5, 5, 128);
@@ -575,7 +584,7 @@ extern "C" int gb200_attn_xm(int device, const gb200_head_operand* L, const floa
     do {                                                                                                \
         if (smem > 48 * 1024)                                                                           \
             cudaFuncSetAttribute(xm_kernel<DPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        xm_kernel<DPV><<<grid, 256, smem, st>>>(l, pos, M, transM, p, dk, H, n, out, ldo, ocol0,          \
+        launch_pdl(xm_kernel<DPV>, grid, 256, smem, st, l, pos, M, transM, p, dk, H, n, out, ldo, ocol0,          \
                                                out_augmented, out_scale);                               \
     } while (0)
     if (dp == 32) LAUNCH_XM(32);

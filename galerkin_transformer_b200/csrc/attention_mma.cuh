@@ -64,6 +64,7 @@ template <int MT, int NT>
 __global__ void __launch_bounds__(256, 3) xty_mma_kernel(HeadOperand L, HeadOperand R, const float* __restrict__ pos,
                                                       int p, int dk, int H, int n, int nsplit, int chunk,
                                                       float* __restrict__ part) {
+    pdl_enter();
     constexpr int TC = 64;                         // tokens per stage (8 k-steps of the m16n8k8 MMA)
     constexpr int DM = 16 * MT, DN = 8 * NT;
     constexpr int LS = DM + 8 - (DM % 32 == 8 ? 0 : 0), RS = DN;   // pitches: see bank note below
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(TT * 2) xm_mma_kernel(HeadOperand L, const flo
                                                      const float* __restrict__ Mat, int transM, int p, int dk, int H,
                                                      int n, float* __restrict__ out, int ldo, int ocol0,
                                                      int out_augmented, float oscale) {
+    pdl_enter();
     constexpr int DK = 8 * KT, DN = 8 * NT, NTHR = TT * 2;   // TT/16 warps, 16 tokens each
     constexpr int LP = (DK % 32 == 4) ? DK : DK + ((4 - DK % 32 + 32) % 32);    // A frag: [token g][feat tq]
     constexpr int MP = (DN % 32 == 8) ? DN : DN + ((8 - DN % 32 + 32) % 32);    // B frag: [feat tq][col g]

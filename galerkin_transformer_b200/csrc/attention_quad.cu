@@ -121,6 +121,7 @@ __device__ __forceinline__ void store_rows(const float (&acc)[4][DP / 16], const
 // mode 1: dQ pass  (rows = queries, streams K,V): dQ = dSp K,  dSp from (dO, V)
 template <int DP, int MODE>
 __global__ void __launch_bounds__(256) quad_rows_kernel(QuadArgs a) {
+    pdl_enter();
     extern __shared__ float sm[];
     float* Xs = sm;                          // Q tile (mode 0) / dO tile (mode 1)
     float* Ks = Xs + QT * (DP + 1);
@@ -159,6 +160,7 @@ __global__ void __launch_bounds__(256) quad_rows_kernel(QuadArgs a) {
 // dK/dV pass (rows = keys, streams Q, dO):  dV = S^T dO,  dK = dSp^T Q
 template <int DP>
 __global__ void __launch_bounds__(256) quad_cols_kernel(QuadArgs a) {
+    pdl_enter();
     extern __shared__ float sm[];
     float* Ks = sm;
     float* Vs = Ks + QT * (DP + 1);
@@ -219,7 +221,7 @@ template <typename K>
 static void launch_quad(K kernel, const QuadArgs& a, size_t smem, cudaStream_t st) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(cdiv(a.n, QT), a.B * a.H);
-    kernel<<<grid, 256, smem, st>>>(a);
+    launch_pdl(kernel, grid, 256, smem, st, a);
 }
 
 extern "C" int gb200_fourier_quad_fwd(int device, const gb200_head_operand* q, const gb200_head_operand* k,

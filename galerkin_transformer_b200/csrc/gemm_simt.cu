@@ -44,6 +44,7 @@ __device__ __forceinline__ float4 load4(const float* base, long long row, int ld
 
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmArgs g) {
+    pdl_enter();
     __shared__ __align__(16) float As[2][BK][BM + PAD];
     __shared__ __align__(16) float Bs[2][BK][BN + PAD];
     const int tid = threadIdx.x;
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmArgs g) {
 
 // fixed-order sum of the split-K partials followed by the epilogue (run-to-run deterministic)
 __global__ void splitk_reduce_kernel(GemmArgs g) {
+    pdl_enter();
     const long long total = (long long)g.nbatch * g.M * g.N;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x) {
@@ -143,6 +145,7 @@ __global__ void splitk_reduce_kernel(GemmArgs g) {
 // column sums of a row-major [M,N] matrix (bias gradients), two deterministic stages
 __global__ void colsum_partial_kernel(const float* __restrict__ X, int M, int N, int ld,
                                       int rows_per_block, float* __restrict__ part) {
+    pdl_enter();
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     const int r0 = blockIdx.y * rows_per_block;
     const int r1 = min(M, r0 + rows_per_block);
@@ -161,6 +164,7 @@ __global__ void colsum_partial_kernel(const float* __restrict__ X, int M, int N,
 }
 __global__ void colsum_final_kernel(const float* __restrict__ part, int nparts, int N, float scale,
                                     int accumulate, float* __restrict__ out) {
+    pdl_enter();
     reduce_partials_2d(part, nparts, N, N, scale, accumulate, out);
 }
 
@@ -169,6 +173,7 @@ __global__ void epilogue_bwd_kernel(const float* __restrict__ dy, int lddy, cons
                                     int ldz, const float* __restrict__ y, int ldy, float* __restrict__ gout,
                                     int ldg, long long M, int N, int act, float rscale, float drop_p,
                                     unsigned long long seed, const unsigned long long* seed_off) {
+    pdl_enter();
     const long long total = M * N;
     if (drop_p > 0.f && seed_off) seed += *seed_off;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
@@ -193,6 +198,7 @@ template <int ACT>
 __global__ void epilogue_bwd_vec4_kernel(const float4* __restrict__ dy, const float4* __restrict__ ref,
                                          float4* __restrict__ gout, unsigned int total4, float rscale, float drop_p,
                                          unsigned long long seed, const unsigned long long* seed_off) {
+    pdl_enter();
     if (drop_p > 0.f && seed_off) seed += *seed_off;
     for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < total4; e += gridDim.x * blockDim.x) {
         float4 v = dy[e];
@@ -224,6 +230,7 @@ __global__ void __launch_bounds__(256) epilogue_bwd_bias_kernel(const float4* __
                                                                 float drop_p, unsigned long long seed,
                                                                 const unsigned long long* seed_off,
                                                                 float* __restrict__ part) {
+    pdl_enter();
     __shared__ float4 red[256];
     if (drop_p > 0.f && seed_off) seed += *seed_off;
     const int rowq = N / 4, q = threadIdx.x % rowq, rsub = threadIdx.x / rowq, rpb = 256 / rowq;
@@ -312,15 +319,15 @@ extern "C" int gb200_gemm(int device, const float* A, int lda, int transA, const
     dim3 grid(cdiv(N, BN), cdiv(M, BM), nbatch * ksplit);
     GB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gb200_gemm: grid too large");
     cudaStream_t st = as_stream(stream);
-    if (!transA && !transB) gemm_simt_kernel<false, false><<<grid, NT, 0, st>>>(g);
-    else if (!transA && transB) gemm_simt_kernel<false, true><<<grid, NT, 0, st>>>(g);
-    else if (transA && !transB) gemm_simt_kernel<true, false><<<grid, NT, 0, st>>>(g);
-    else gemm_simt_kernel<true, true><<<grid, NT, 0, st>>>(g);
+    if (!transA && !transB) launch_pdl(gemm_simt_kernel<false, false>, grid, NT, 0, st, g);
+    else if (!transA && transB) launch_pdl(gemm_simt_kernel<false, true>, grid, NT, 0, st, g);
+    else if (transA && !transB) launch_pdl(gemm_simt_kernel<true, false>, grid, NT, 0, st, g);
+    else launch_pdl(gemm_simt_kernel<true, true>, grid, NT, 0, st, g);
     if (ksplit > 1) {
         long long total = (long long)nbatch * M * N;
         int blocks = (int)((total + 255) / 256);
         if (blocks > 148 * 8) blocks = 148 * 8;
-        splitk_reduce_kernel<<<blocks, 256, 0, st>>>(g);
+        launch_pdl(splitk_reduce_kernel, blocks, 256, 0, st, g);
     }
     return check_launch("gb200_gemm", ksplit > 1 ? 2 : 1);
 }
@@ -341,9 +348,9 @@ extern "C" int gb200_colsum(int device, const float* X, int ld, long long M, int
                "gb200_colsum: workspace too small");
     GB_REQUIRE(nparts <= 65535, "gb200_colsum: too many rows");
     cudaStream_t st = as_stream(stream);
-    colsum_partial_kernel<<<dim3(cdiv(N, 32), nparts), dim3(32, 32), 0, st>>>(X, (int)M, N, ld, rows_per_block,
+    launch_pdl(colsum_partial_kernel, dim3(cdiv(N, 32), nparts), dim3(32, 32), 0, st, X, (int)M, N, ld, rows_per_block,
                                                                                workspace);
-    colsum_final_kernel<<<cdiv(N, 32), dim3(32, 32), 0, st>>>(workspace, nparts, N, scale, accumulate, out);
+    launch_pdl(colsum_final_kernel, cdiv(N, 32), dim3(32, 32), 0, st, workspace, nparts, N, scale, accumulate, out);
     return check_launch("gb200_colsum", 2);
 }
 
@@ -369,16 +376,16 @@ extern "C" int gb200_epilogue_bwd(int device, const float* dy, int lddy, const f
         float4* g4 = reinterpret_cast<float4*>(g);
         cudaStream_t st = as_stream(stream);
         if (act == ACT_RELU)
-            epilogue_bwd_vec4_kernel<ACT_RELU><<<blocks, 256, 0, st>>>(d4, r4, g4, total4, rscale, drop_p, seed, rng_offset_ptr());
+            launch_pdl(epilogue_bwd_vec4_kernel<ACT_RELU>, blocks, 256, 0, st, d4, r4, g4, total4, rscale, drop_p, seed, rng_offset_ptr());
         else if (act == ACT_SILU)
-            epilogue_bwd_vec4_kernel<ACT_SILU><<<blocks, 256, 0, st>>>(d4, r4, g4, total4, rscale, drop_p, seed, rng_offset_ptr());
+            launch_pdl(epilogue_bwd_vec4_kernel<ACT_SILU>, blocks, 256, 0, st, d4, r4, g4, total4, rscale, drop_p, seed, rng_offset_ptr());
         else
-            epilogue_bwd_vec4_kernel<ACT_NONE><<<blocks, 256, 0, st>>>(d4, r4, g4, total4, rscale, drop_p, seed, rng_offset_ptr());
+            launch_pdl(epilogue_bwd_vec4_kernel<ACT_NONE>, blocks, 256, 0, st, d4, r4, g4, total4, rscale, drop_p, seed, rng_offset_ptr());
         return check_launch("gb200_epilogue_bwd");
     }
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    epilogue_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(dy, lddy, z, ldz, y, ldy, g, ldg, M, N, act,
+    launch_pdl(epilogue_bwd_kernel, blocks, 256, 0, as_stream(stream), dy, lddy, z, ldz, y, ldy, g, ldg, M, N, act,
                                                                rscale, drop_p, seed, rng_offset_ptr());
     return check_launch("gb200_epilogue_bwd");
 }
@@ -419,14 +426,14 @@ extern "C" int gb200_epilogue_bwd_bias(int device, const float* dy, int lddy, co
     const float4* r4 = reinterpret_cast<const float4*>(ref);
     float4* g4 = reinterpret_cast<float4*>(g);
     if (act == ACT_RELU)
-        epilogue_bwd_bias_kernel<ACT_RELU><<<blocks, 256, 0, st>>>(d4, r4, g4, (int)M, N, rscale, drop_p, seed,
+        launch_pdl(epilogue_bwd_bias_kernel<ACT_RELU>, blocks, 256, 0, st, d4, r4, g4, (int)M, N, rscale, drop_p, seed,
                                                                    rng_offset_ptr(), workspace);
     else if (act == ACT_SILU)
-        epilogue_bwd_bias_kernel<ACT_SILU><<<blocks, 256, 0, st>>>(d4, r4, g4, (int)M, N, rscale, drop_p, seed,
+        launch_pdl(epilogue_bwd_bias_kernel<ACT_SILU>, blocks, 256, 0, st, d4, r4, g4, (int)M, N, rscale, drop_p, seed,
                                                                    rng_offset_ptr(), workspace);
     else
-        epilogue_bwd_bias_kernel<ACT_NONE><<<blocks, 256, 0, st>>>(d4, r4, g4, (int)M, N, rscale, drop_p, seed,
+        launch_pdl(epilogue_bwd_bias_kernel<ACT_NONE>, blocks, 256, 0, st, d4, r4, g4, (int)M, N, rscale, drop_p, seed,
                                                                    rng_offset_ptr(), workspace);
-    colsum_final_kernel<<<cdiv(N, 32), dim3(32, 32), 0, st>>>(workspace, blocks, N, 1.f, 0, dbias);
+    launch_pdl(colsum_final_kernel, cdiv(N, 32), dim3(32, 32), 0, st, workspace, blocks, N, 1.f, 0, dbias);
     return check_launch("gb200_epilogue_bwd_bias", 2);
 }

@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     const int kbeg = split * g.kchunk;
     const int kend = min(g.K, kbeg + g.kchunk);
     const int nkb = (kend - kbeg + TC_BK - 1) / TC_BK;
+    if (GB200_PDL_MODE == 1) pdl_trigger_now();
     if (threadIdx.x == 64) tc_stamp(g, 0);                                   // CTA entry
 
     if (threadIdx.x == 0) {
@@ -252,6 +253,9 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Everything above (barrier init, TMEM allocation, tensor-map prefetch) touched no global memory and has
+    // overlapped the tail of the previous kernel; from here on its results are needed.
+    pdl_wait();
     if (threadIdx.x == 64) tc_stamp(g, 1);                                   // barriers + TMEM ready
 
     if (warp == 0) {
@@ -351,6 +355,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
             tc_fence_after();
         }
         if (threadIdx.x == 64) tc_stamp(g, 5);                               // accumulator complete
+        if (GB200_PDL_MODE == 2 && threadIdx.x == 64) pdl_trigger_now();
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t v[32];
@@ -483,6 +488,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_persistent_kernel(cons
     const int ntn = (g.N + BN - 1) / BN, ntm = (g.M + TC_BM - 1) / TC_BM;
     const int ntiles = ntn * ntm;
     const int nkb = (g.K + TC_BK - 1) / TC_BK;
+    pdl_trigger();
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TCP_STAGES; ++s) {
@@ -508,6 +514,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_persistent_kernel(cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {   // ---------------- TMA producer ----------------
@@ -668,6 +675,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_persistent_kernel(cons
 }
 
 __global__ void tc_splitk_reduce_kernel(TcArgs g) {
+    pdl_enter();
     const long long total = (long long)g.M * g.N;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x) {
@@ -722,7 +730,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs&
         configured = true;
     }
     dim3 grid(cdiv(g.N, BN), cdiv(g.M, TC_BM), g.ksplit);
-    gemm_tc_kernel<BN, A_MN, B_MN><<<grid, TC_THREADS, smem, st>>>(ma, mb, g);
+    launch_pdl(gemm_tc_kernel<BN, A_MN, B_MN>, grid, TC_THREADS, smem, st, ma, mb, g);
     return 0;
 }
 
@@ -743,7 +751,7 @@ static int launch_tc_persistent(const CUtensorMap& ma, const CUtensorMap& mb, co
     }
     const int tiles = cdiv(g.N, BN) * cdiv(g.M, TC_BM);
     const int grid = tiles < num_sms ? tiles : num_sms;
-    gemm_tc_persistent_kernel<BN, A_MN, B_MN><<<grid, TCP_THREADS, smem, st>>>(ma, mb, g);
+    launch_pdl(gemm_tc_persistent_kernel<BN, A_MN, B_MN>, grid, TCP_THREADS, smem, st, ma, mb, g);
     return 0;
 }
 
@@ -860,7 +868,7 @@ extern "C" int gb200_gemm_tc(int device, const float* A, int lda, int transA, co
         long long total = (long long)M * N;
         int blocks = (int)((total + 255) / 256);
         if (blocks > 148 * 8) blocks = 148 * 8;
-        tc_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(g);
+        launch_pdl(tc_splitk_reduce_kernel, blocks, 256, 0, st, g);
     }
     return check_launch("gb200_gemm_tc", g.ksplit > 1 ? 2 : 1);
 }

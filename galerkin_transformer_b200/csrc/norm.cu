@@ -12,6 +12,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_fwd_kernel(
     const float* __restrict__ x, long long rows, int width, const float* __restrict__ gamma,
     const float* __restrict__ beta, float eps, float* __restrict__ y, float* __restrict__ mean_out,
     float* __restrict__ rstd_out) {
+    pdl_enter();
     const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
     for (long long r = (long long)blockIdx.x * LN_WARPS + warp; r < rows; r += (long long)gridDim.x * LN_WARPS) {
         const float* xr = x + r * width;
@@ -31,6 +32,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(
     const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ rstd, const float* __restrict__ gamma, long long rows, int width,
     float* __restrict__ dx, float* __restrict__ part) {
+    pdl_enter();
     extern __shared__ float sm[];   // [LN_WARPS][2][width]
     const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
     float* sg = sm + (size_t)warp * 2 * width;
@@ -69,6 +71,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_bwd_kernel(
 __global__ void layernorm_bwd_reduce_kernel(const float* __restrict__ part, int nblocks, int width,
                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
                                             int accumulate) {
+    pdl_enter();
     reduce_partials_2d(part + (long long)blockIdx.y * width, nblocks, 2LL * width, width, 1.f, accumulate,
                        blockIdx.y == 0 ? dgamma : dbeta);
 }
@@ -88,7 +91,7 @@ extern "C" int gb200_layernorm_fwd(int device, const float* x, long long rows, i
     use_device(device);
     GB_REQUIRE(x && gamma && beta && y && mean && rstd && width >= 1, "gb200_layernorm_fwd: bad arguments");
     if (rows == 0) return GB200_OK;
-    layernorm_fwd_kernel<<<ln_blocks(rows), LN_WARPS * 32, 0, as_stream(stream)>>>(x, rows, width, gamma, beta,
+    launch_pdl(layernorm_fwd_kernel, ln_blocks(rows), LN_WARPS * 32, 0, as_stream(stream), x, rows, width, gamma, beta,
                                                                                   eps, y, mean, rstd);
     return check_launch("gb200_layernorm_fwd");
 }
@@ -112,8 +115,8 @@ extern "C" int gb200_layernorm_bwd(int device, const float* dy, const float* x, 
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaStream_t st = as_stream(stream);
-    layernorm_bwd_kernel<<<nblocks, LN_WARPS * 32, smem, st>>>(dy, x, mean, rstd, gamma, rows, width, dx, workspace);
-    layernorm_bwd_reduce_kernel<<<dim3(cdiv(width, 32), 2), dim3(32, 32), 0, st>>>(workspace, nblocks, width, dgamma,
+    launch_pdl(layernorm_bwd_kernel, nblocks, LN_WARPS * 32, smem, st, dy, x, mean, rstd, gamma, rows, width, dx, workspace);
+    launch_pdl(layernorm_bwd_reduce_kernel, dim3(cdiv(width, 32), 2), dim3(32, 32), 0, st, workspace, nblocks, width, dgamma,
                                                                                 dbeta, accumulate);
     return check_launch("gb200_layernorm_bwd", 2);
 }

@@ -1,6 +1,7 @@
 // Library-level plumbing: error strings, device selection, launch accounting.
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -12,6 +13,14 @@ static std::atomic<unsigned long long> g_launches{0};
 static const unsigned long long* g_rng_offset = nullptr;
 
 const unsigned long long* rng_offset_ptr() { return g_rng_offset; }
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("GB200_PDL");      // opt-in: measured SLOWER inside the captured step
+        return e && e[0] == '1';
+    }();
+    return on;
+}
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -54,6 +63,7 @@ namespace gb200 {
 constexpr int PACK_MAX = 64;
 struct PackArgs { const float* src[PACK_MAX]; long long off[PACK_MAX + 1]; };
 __global__ void pack_kernel(PackArgs a, float* __restrict__ dst) {
+    pdl_enter();
     const int seg = blockIdx.x;
     const float* s = a.src[seg];
     float* d = dst + a.off[seg];
@@ -78,6 +88,6 @@ extern "C" int gb200_pack(int device, float* dst, const float* const* srcs, cons
     int by = (int)((biggest + 256 * 8 - 1) / (256 * 8));
     if (by < 1) by = 1;
     if (by > 32) by = 32;
-    pack_kernel<<<dim3(n, by), 256, 0, as_stream(stream)>>>(a, dst);
+    launch_pdl(pack_kernel, dim3(n, by), 256, 0, as_stream(stream), a, dst);
     return check_launch("gb200_pack");
 }

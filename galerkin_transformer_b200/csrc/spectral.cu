@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(128) ydft_kernel(const float* __restrict__ x, 
                                                    const float2* __restrict__ twY, float scale, int hermitian,
                                                    int nsplit, int ychunk, float2* __restrict__ out,
                                                    float2* __restrict__ part) {
+    pdl_enter();
     __shared__ float2 tws[KYG][YCH];
     const int kg0 = blockIdx.z * KYG;
     const int nk = min(KYG, m - kg0);
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(128) ydft_kernel(const float* __restrict__ x, 
 
 __global__ void ydft_reduce_kernel(const float2* __restrict__ part, int nsplit, long long total, int C, int m,
                                    int n, float scale, int hermitian, float2* __restrict__ out) {
+    pdl_enter();
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x) {
         const int ky = (int)((e / C) % m);
@@ -102,6 +104,7 @@ __global__ void ydft_reduce_kernel(const float2* __restrict__ part, int nsplit, 
 // thread per (b, r, ky, c); loops over X
 __global__ void xdft_kernel(const float2* __restrict__ T1, int B, int n, int m, int C,
                             const float2* __restrict__ twX, float scale, float2* __restrict__ out) {
+    pdl_enter();
     const long long total = (long long)B * 2 * m * m * C;
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
@@ -126,6 +129,7 @@ __global__ void xdft_kernel(const float2* __restrict__ T1, int B, int n, int m, 
 // thread per (b, X, ky, c); loops over r
 __global__ void xidft_kernel(const float2* __restrict__ Oft, int B, int n, int m, int C,
                              const float2* __restrict__ twX, float scale, float2* __restrict__ Z) {
+    pdl_enter();
     const long long total = (long long)B * n * m * C;
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
@@ -154,6 +158,7 @@ constexpr int MIXB = 2;    // batch entries per thread: small, so the grid has e
 __global__ void mix_fwd_kernel(const float2* __restrict__ Xf, const float2* __restrict__ W0,
                                const float2* __restrict__ W1, int B, int halves, int M2, int Ci, int Co,
                                float2* __restrict__ Of) {
+    pdl_enter();
     const int mode = blockIdx.x * blockDim.x + threadIdx.x;
     const int o = blockIdx.y, half = blockIdx.z % halves, b0 = (blockIdx.z / halves) * MIXB;
     if (mode >= M2) return;
@@ -181,6 +186,7 @@ __global__ void mix_fwd_kernel(const float2* __restrict__ Xf, const float2* __re
 __global__ void mix_bwd_x_kernel(const float2* __restrict__ dO, const float2* __restrict__ W0,
                                  const float2* __restrict__ W1, int B, int halves, int M2, int Ci, int Co,
                                  float2* __restrict__ dX) {
+    pdl_enter();
     const int mode = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y, half = blockIdx.z % halves, b0 = (blockIdx.z / halves) * MIXB;
     if (mode >= M2) return;
@@ -208,6 +214,7 @@ __global__ void mix_bwd_x_kernel(const float2* __restrict__ dO, const float2* __
 __global__ void mix_bwd_w_kernel(const float2* __restrict__ Xf, const float2* __restrict__ dO, int B,
                                  int halves, int M2, int Ci, int Co, float2* __restrict__ dW0,
                                  float2* __restrict__ dW1, int accumulate) {
+    pdl_enter();
     const int mode = blockIdx.x * blockDim.x + threadIdx.x;
     const int o = blockIdx.y, half = blockIdx.z;
     if (mode >= M2) return;
@@ -239,6 +246,7 @@ __global__ void __launch_bounds__(256) yidft_epi_kernel(
     int hermitian, const float* __restrict__ x2, int Ci, const float* __restrict__ Wm,
     const float* __restrict__ bias, int act, float* __restrict__ y, float* __restrict__ zout,
     int tiles_per_cta) {
+    pdl_enter();
     extern __shared__ __align__(16) float sm[];
     float* twc = sm;                                            // [m][YT]  cos * c_ky * scale
     float* tws = twc + m * YT;                                  // [m][YT]  sin * c_ky * scale
@@ -340,7 +348,7 @@ extern "C" int gb200_spectral_ydft(int device, const float* x, long long R, int 
     do {                                                                                                       \
         if (smem > 48 * 1024)                                                                                  \
             cudaFuncSetAttribute(ydft_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        ydft_mma_kernel<NT><<<grid, SM_WARPS * 32, smem, st>>>(x, R, n, C, m, reinterpret_cast<const float2*>(twY), \
+        launch_pdl(ydft_mma_kernel<NT>, grid, SM_WARPS * 32, smem, st, x, R, n, C, m, reinterpret_cast<const float2*>(twY), \
                                                               scale, hermitian, reinterpret_cast<float2*>(out)); \
     } while (0)
         switch (C / 8) { case 1: YD(1); break; case 2: YD(2); break; case 3: YD(3); break; case 4: YD(4); break;
@@ -353,14 +361,14 @@ extern "C" int gb200_spectral_ydft(int device, const float* x, long long R, int 
     nsplit = cdiv(n, ychunk);
     dim3 grid(cdiv(RC, 128), nsplit, cdiv(m, KYG));
     GB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gb200_spectral_ydft: grid too large");
-    ydft_kernel<<<grid, 128, 0, st>>>(x, RC, C, n, m, reinterpret_cast<const float2*>(twY), scale, hermitian,
+    launch_pdl(ydft_kernel, grid, 128, 0, st, x, RC, C, n, m, reinterpret_cast<const float2*>(twY), scale, hermitian,
                                       nsplit, ychunk, reinterpret_cast<float2*>(out),
                                       reinterpret_cast<float2*>(workspace));
     if (nsplit > 1) {
         long long total = R * m * C;
         int blocks = (int)((total + 255) / 256);
         if (blocks > 148 * 8) blocks = 148 * 8;
-        ydft_reduce_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float2*>(workspace), nsplit, total, C,
+        launch_pdl(ydft_reduce_kernel, blocks, 256, 0, st, reinterpret_cast<const float2*>(workspace), nsplit, total, C,
                                                    m, n, scale, hermitian, reinterpret_cast<float2*>(out));
     }
     return check_launch("gb200_spectral_ydft", nsplit > 1 ? 2 : 1);
@@ -374,12 +382,12 @@ extern "C" int gb200_spectral_xdft(int device, const float* T1, int B, int n, in
     cudaStream_t st = as_stream(stream);
     if (!inverse) {
         long long total = (long long)B * 2 * m * m * C;
-        xdft_kernel<<<cdiv(total, 128), 128, 0, st>>>(reinterpret_cast<const float2*>(T1), B, n, m, C,
+        launch_pdl(xdft_kernel, cdiv(total, 128), 128, 0, st, reinterpret_cast<const float2*>(T1), B, n, m, C,
                                                       reinterpret_cast<const float2*>(twX), scale,
                                                       reinterpret_cast<float2*>(out));
     } else {
         long long total = (long long)B * n * m * C;
-        xidft_kernel<<<cdiv(total, 256), 256, 0, st>>>(reinterpret_cast<const float2*>(T1), B, n, m, C,
+        launch_pdl(xidft_kernel, cdiv(total, 256), 256, 0, st, reinterpret_cast<const float2*>(T1), B, n, m, C,
                                                        reinterpret_cast<const float2*>(twX), scale,
                                                        reinterpret_cast<float2*>(out));
     }
@@ -395,7 +403,7 @@ extern "C" int gb200_spectral_mix_fwd(int device, const float* Xf, const float* 
     int th = mix_threads(M2);
     dim3 grid(cdiv(M2, th), Co, halves * cdiv(B, MIXB));
     GB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gb200_spectral_mix_fwd: grid too large");
-    mix_fwd_kernel<<<grid, th, 0, as_stream(stream)>>>(reinterpret_cast<const float2*>(Xf),
+    launch_pdl(mix_fwd_kernel, grid, th, 0, as_stream(stream), reinterpret_cast<const float2*>(Xf),
                                                        reinterpret_cast<const float2*>(W0),
                                                        reinterpret_cast<const float2*>(W1), B, halves, M2, Ci, Co,
                                                        reinterpret_cast<float2*>(Of));
@@ -411,7 +419,7 @@ extern "C" int gb200_spectral_mix_bwd(int device, const float* Xf, const float* 
     cudaStream_t st = as_stream(stream);
     if (dX) {
         dim3 grid(cdiv(M2, th), Ci, halves * cdiv(B, MIXB));
-        mix_bwd_x_kernel<<<grid, th, 0, st>>>(reinterpret_cast<const float2*>(dO),
+        launch_pdl(mix_bwd_x_kernel, grid, th, 0, st, reinterpret_cast<const float2*>(dO),
                                               reinterpret_cast<const float2*>(W0),
                                               reinterpret_cast<const float2*>(W1), B, halves, M2, Ci, Co,
                                               reinterpret_cast<float2*>(dX));
@@ -419,7 +427,7 @@ extern "C" int gb200_spectral_mix_bwd(int device, const float* Xf, const float* 
     if (dW0) {
         GB_REQUIRE(halves == 1 || dW1, "gb200_spectral_mix_bwd: dW1 is null");
         dim3 grid(cdiv(M2, th), Co, halves);
-        mix_bwd_w_kernel<<<grid, th, 0, st>>>(reinterpret_cast<const float2*>(Xf),
+        launch_pdl(mix_bwd_w_kernel, grid, th, 0, st, reinterpret_cast<const float2*>(Xf),
                                               reinterpret_cast<const float2*>(dO), B, halves, M2, Ci, Co,
                                               reinterpret_cast<float2*>(dW0), reinterpret_cast<float2*>(dW1),
                                               accumulate_dw);
@@ -453,7 +461,7 @@ extern "C" int gb200_spectral_yidft_epilogue(int device, const float* Z, long lo
     do {                                                                                                         \
         if (smem2 > 48 * 1024)                                                                                   \
             cudaFuncSetAttribute(yidft_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2); \
-        yidft_mma_kernel<NT><<<grid, SM_WARPS * 32, smem2, st2>>>(                                               \
+        launch_pdl(yidft_mma_kernel<NT>, grid, SM_WARPS * 32, smem2, st2, \
             reinterpret_cast<const float2*>(Z), R, n, m, Co, reinterpret_cast<const float2*>(twY), scale, hermitian, \
             x2, Ci, Wm, bias, act, y, zout, tiles_per_warp, chunks);                                             \
     } while (0)
@@ -472,7 +480,7 @@ extern "C" int gb200_spectral_yidft_epilogue(int device, const float* Z, long lo
     int tiles_per_cta = ntiles;
     while (tiles_per_cta > 1 && R * cdiv(ntiles, tiles_per_cta) < 4 * 148) tiles_per_cta = (tiles_per_cta + 1) / 2;
     dim3 grid((unsigned)R, cdiv(ntiles, tiles_per_cta));
-    yidft_epi_kernel<<<grid, 256, smem, as_stream(stream)>>>(reinterpret_cast<const float2*>(Z), n, m, Co,
+    launch_pdl(yidft_epi_kernel, grid, 256, smem, as_stream(stream), reinterpret_cast<const float2*>(Z), n, m, Co,
                                                             reinterpret_cast<const float2*>(twY), scale, hermitian,
                                                             x2, Ci, Wm, bias, act, y, zout, tiles_per_cta);
     return check_launch("gb200_spectral_yidft_epilogue");

@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(SM_WARPS * 32) ydft_mma_kernel(const float* __
                                                                  int C, int m, const float2* __restrict__ twY,
                                                                  float scale, int hermitian,
                                                                  float2* __restrict__ out) {
+    pdl_enter();
     extern __shared__ float As[];                  // [32][AP]  rows j: cos(ky=j) | -sin(ky=j-m) | 0
     const int KP = (n + 7) / 8 * 8;
     const int AP = KP + ((4 - KP % 32 + 32) % 32 == 0 ? 0 : ((4 - KP % 32 + 32) % 32));   // pitch = 4 (mod 32)
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(SM_WARPS * 32) yidft_mma_kernel(
     int hermitian, const float* __restrict__ x2, int Ci, const float* __restrict__ Wm,
     const float* __restrict__ bias, int act, float* __restrict__ y, float* __restrict__ zout, int tiles_per_warp,
     int chunks_per_row) {
+    pdl_enter();
     extern __shared__ float A2[];                  // [MP][SP]: twiddle part of the A operand, rows Y
     const int KS = (2 * m + 7) / 8 * 8;            // spectral K, padded
     const int KC = (Ci + 7) / 8 * 8;               // channel K, padded
