@@ -142,6 +142,135 @@ __global__ void splitk_reduce_kernel(GemmArgs g) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Degenerate shapes (single batch).  A 64 x 64 tile wastes 63/64 of its work on an N = 1 output head and cannot
+// spread a 159 048-long reduction with a 128-element result over the machine; these three kernels are pure
+// streaming passes over the one large operand (the C3 regressor: libs/model.py:615-617 `fc(cat[x, grid])` grid
+// columns, :629 `out` Linear(dim_feedforward, 1), and their gradients).
+//   op(A)(m,k) = A[m*sam + k*sak],  op(B)(k,n) = B[k*sbk + n*sbn]
+// ---------------------------------------------------------------------------------------------------------
+struct SkinnyArgs {
+    const float* A; const float* B;
+    int M, N, K;
+    long long sam, sak, sbk, sbn;
+    int ksplit, kchunk;
+    GemmEpilogue ep;
+    float* ws;
+};
+
+// (1) tiny inner dimension (K <= 8): one output element per thread, op(A) row held in registers
+__global__ void __launch_bounds__(256) gemm_thin_k_kernel(SkinnyArgs g) {
+    pdl_enter();
+    const unsigned total = (unsigned)g.M * (unsigned)g.N;          // host guarantees M*N < 2^31
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int m = (int)(e / (unsigned)g.N), n = (int)(e % (unsigned)g.N);
+        float acc = 0.f;
+        for (int k = 0; k < g.K; ++k) acc = fmaf(g.A[m * g.sam + k * g.sak], g.B[k * g.sbk + n * g.sbn], acc);
+        g.ep.store(0, m, n, g.M, g.N, acc);
+    }
+}
+
+// (2) tiny output width (N <= 8), row-major A: one warp per output row, lanes stride the contraction
+template <int NMAX>
+__global__ void __launch_bounds__(256) gemm_thin_n_kernel(SkinnyArgs g) {
+    pdl_enter();
+    const int lane = threadIdx.x % 32;
+    const int wglobal = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, nwarps = gridDim.x * (blockDim.x / 32);
+    for (int m = wglobal; m < g.M; m += nwarps) {
+        float acc[NMAX];
+#pragma unroll
+        for (int n = 0; n < NMAX; ++n) acc[n] = 0.f;
+        const float* a = g.A + m * g.sam;
+        for (int k = lane; k < g.K; k += 32) {
+            const float av = a[k];
+#pragma unroll
+            for (int n = 0; n < NMAX; ++n)
+                if (n < g.N) acc[n] = fmaf(av, g.B[k * g.sbk + n * g.sbn], acc[n]);
+        }
+#pragma unroll
+        for (int n = 0; n < NMAX; ++n) {
+            const float s = warp_sum(acc[n]);
+            if (lane == n && n < g.N) g.ep.store(0, m, n, g.M, g.N, s);
+        }
+    }
+}
+
+// (3) tiny output (M*N <= 1024), very long contraction, both operands stored k-major (the weight-gradient layout
+// dY^T X): CTA `split` owns k in [split*kchunk, ...), threads own output elements, several k-rows in flight per CTA;
+// partial sums go to ws[split][M*N] and are finished in fixed order by tall_final_kernel.
+__global__ void __launch_bounds__(256) gemm_tall_partial_kernel(SkinnyArgs g) {
+    pdl_enter();
+    __shared__ float red[256];
+    const int E = g.M * g.N;
+    const int le = E < 256 ? E : 256;                 // threads along the output
+    const int KP = 256 / le;                          // k-rows processed concurrently
+    const int kk = threadIdx.x / le, e0 = threadIdx.x % le;
+    const bool active = kk < KP;
+    const int kbeg = blockIdx.x * g.kchunk, kend = min(g.K, kbeg + g.kchunk);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* ap[4]; const float* bp[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int e = e0 + j * le;
+        const int m = e < E ? e / g.N : 0, n = e < E ? e % g.N : 0;
+        ap[j] = g.A + m * g.sam;
+        bp[j] = g.B + n * g.sbn;
+    }
+    const int nj = (E + le - 1) / le;                 // <= 4
+    if (active) {
+        int k = kbeg + kk;
+        for (; k + 3 * KP < kend; k += 4 * KP) {      // four independent k-rows per thread in flight
+            float av[4][4], bv[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (j < nj) {
+                        av[u][j] = ap[j][(long long)(k + u * KP) * g.sak];
+                        bv[u][j] = bp[j][(long long)(k + u * KP) * g.sbk];
+                    }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (j < nj) acc[j] = fmaf(av[u][j], bv[u][j], acc[j]);
+        }
+        for (; k < kend; k += KP)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < nj) acc[j] = fmaf(ap[j][(long long)k * g.sak], bp[j][(long long)k * g.sbk], acc[j]);
+    }
+    // fold the KP concurrent k-rows (fixed order), one output slot j at a time
+    for (int j = 0; j < nj; ++j) {
+        red[threadIdx.x] = active ? acc[j] : 0.f;
+        __syncthreads();
+        if (kk == 0) {
+            float s = 0.f;
+            for (int q = 0; q < KP; ++q) s += red[q * le + e0];
+            const int e = e0 + j * le;
+            if (e < E) g.ws[(long long)blockIdx.x * E + e] = s;
+        }
+        __syncthreads();
+    }
+}
+__global__ void gemm_tall_final_kernel(SkinnyArgs g) {
+    pdl_enter();
+    __shared__ float red[32][33];
+    const int E = g.M * g.N;
+    const int e = blockIdx.x * 32 + threadIdx.x;
+    float s = 0.f;
+    if (e < E)
+        for (int p = threadIdx.y; p < g.ksplit; p += 32) s += g.ws[(long long)p * E + e];
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && e < E) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) t += red[i][threadIdx.x];
+        g.ep.store(0, e / g.N, e % g.N, g.M, g.N, t);
+    }
+}
+
 // column sums of a row-major [M,N] matrix (bias gradients), two deterministic stages
 __global__ void colsum_partial_kernel(const float* __restrict__ X, int M, int N, int ld,
                                       int rows_per_block, float* __restrict__ part) {
@@ -277,6 +406,10 @@ extern "C" size_t gb200_gemm_workspace_bytes(int M, int N, int K, int nbatch, in
 }
 
 extern "C" int gb200_gemm_suggest_ksplit(int M, int N, int K, int nbatch) {
+    if (nbatch == 1 && (long long)M * N <= 1024 && K >= 8192) {      // streaming reduction: ~8 CTAs per SM
+        const int s = K / 128;
+        return s > 148 * 8 ? 148 * 8 : s;
+    }
     long long tiles = (long long)cdiv(M, BM) * cdiv(N, BN) * nbatch;
     if (tiles >= 148 || K < 512) return 1;
     int want = (int)((2 * 148 + tiles - 1) / tiles);
@@ -316,9 +449,34 @@ extern "C" int gb200_gemm(int device, const float* A, int lda, int transA, const
     if (ksplit > 1)
         GB_REQUIRE(workspace && workspace_bytes >= gb200_gemm_workspace_bytes(M, N, K, nbatch, ksplit),
                    "gb200_gemm: split-K workspace too small (%zu bytes)", workspace_bytes);
+    cudaStream_t st = as_stream(stream);
+    if (nbatch == 1) {      // degenerate shapes: streaming kernels instead of 64 x 64 tiles
+        SkinnyArgs s;
+        s.A = A; s.B = B; s.M = M; s.N = N; s.K = K; s.ep = g.ep; s.ws = workspace;
+        s.sam = transA ? 1 : lda; s.sak = transA ? lda : 1;
+        s.sbk = transB ? 1 : ldb; s.sbn = transB ? ldb : 1;
+        s.ksplit = ksplit;
+        s.kchunk = cdiv(K > 0 ? K : 1, ksplit);
+        const long long total = (long long)M * N;
+        if (K <= 8 && total < (1ll << 31)) {
+            launch_pdl(gemm_thin_k_kernel, (int)(total / 256 + 1 < 148 * 16 ? total / 256 + 1 : 148 * 16), 256, 0, st, s);
+            return check_launch("gb200_gemm(thin K)", 1);
+        }
+        if (N <= 8 && !transA && M >= 1024) {
+            const int blocks = cdiv(M, 8) < 148 * 16 ? cdiv(M, 8) : 148 * 16;
+            if (N <= 2) launch_pdl(gemm_thin_n_kernel<2>, blocks, 256, 0, st, s);
+            else launch_pdl(gemm_thin_n_kernel<8>, blocks, 256, 0, st, s);
+            return check_launch("gb200_gemm(thin N)", 1);
+        }
+        if (transA && !transB && total <= 1024 && ksplit > 1) {
+            s.ksplit = cdiv(K, s.kchunk);
+            launch_pdl(gemm_tall_partial_kernel, s.ksplit, 256, 0, st, s);
+            launch_pdl(gemm_tall_final_kernel, cdiv(total, 32), dim3(32, 32), 0, st, s);
+            return check_launch("gb200_gemm(tall)", 2);
+        }
+    }
     dim3 grid(cdiv(N, BN), cdiv(M, BM), nbatch * ksplit);
     GB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gb200_gemm: grid too large");
-    cudaStream_t st = as_stream(stream);
     if (!transA && !transB) launch_pdl(gemm_simt_kernel<false, false>, grid, NT, 0, st, g);
     else if (!transA && transB) launch_pdl(gemm_simt_kernel<false, true>, grid, NT, 0, st, g);
     else if (transA && !transB) launch_pdl(gemm_simt_kernel<true, false>, grid, NT, 0, st, g);

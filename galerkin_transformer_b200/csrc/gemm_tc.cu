@@ -30,7 +30,18 @@ namespace gb200 {
 constexpr int TC_BM = 128, TC_BK = 32, TC_THREADS = 192;
 // pipeline depth: 3 stages let two CTAs share an SM (one tile's epilogue overlaps another's main loop); a 6-stage,
 // one-CTA-per-SM ring for the long-K weight-gradient GEMMs was measured and is slower (tools/bench_gemm.py)
-template <bool A_MN, bool B_MN> struct TcStages { static constexpr int value = 3; };   // 6 for MN/MN measured slower
+// (6 for MN/MN measured slower).  Narrow tiles (BN <= 64, 24 KB stages) afford a 4th stage at the same occupancy;
+// the 192-wide tile (N = 384 in one wave of 232 CTAs instead of 348 in two) has room for two.
+#ifndef GB200_TC_STAGES_NARROW
+#define GB200_TC_STAGES_NARROW 4
+#endif
+template <int BN> __host__ __device__ constexpr int tc_stages() { return BN == 192 ? 2 : (BN <= 64 ? GB200_TC_STAGES_NARROW : 3); }
+template <int BN> __host__ __device__ constexpr int tc_tmem_cols() { return BN == 192 ? 256 : BN; }     // power of two >= 32
+template <int BN> __host__ __device__ constexpr int tc_smem_bytes() {
+    constexpr int ring = tc_stages<BN>() * (TC_BM * TC_BK * 4 + BN * TC_BK * 4);
+    constexpr int staging = TC_BM * (BN + 4) * 4;                                   // epilogue reuses the ring
+    return (ring > staging ? ring : staging) + 1024 + 256;
+}
 constexpr uint32_t TC_SPIN_LIMIT = 1u << 26;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -213,11 +224,11 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     constexpr int A_BYTES = TC_BM * TC_BK * 4;          // 16 KB
     constexpr int B_BYTES = BN * TC_BK * 4;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr int TC_STAGES = TcStages<A_MN, B_MN>::value;
+    constexpr int TC_STAGES = tc_stages<BN>();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by SWIZZLE_128B atoms
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * STAGE_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + tc_smem_bytes<BN>() - 1024 - 256);   // past ring AND staging
     uint64_t* empty_bar = full_bar + TC_STAGES;
     uint64_t* conv_bar = empty_bar + TC_STAGES;
     uint64_t* tmem_full = conv_bar + TC_STAGES;
@@ -245,7 +256,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     }
     if (warp == 2) {   // TMEM allocation: BN fp32 columns x 128 lanes (power of two >= 32)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "n"(BN)
+                     "n"(tc_tmem_cols<BN>())
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -451,7 +462,8 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     if (threadIdx.x == 64) tc_stamp(g, 7);                                   // all epilogue stores issued
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(tc_tmem_cols<BN>())
+                     : "memory");
     }
 }
 
@@ -723,7 +735,7 @@ static bool make_map(CUtensorMap* m, const float* base, long long inner, long lo
 
 template <int BN, bool A_MN, bool B_MN>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& g, cudaStream_t st) {
-    constexpr int smem = TcStages<A_MN, B_MN>::value * (TC_BM * TC_BK * 4 + BN * TC_BK * 4) + 1024 + 256;
+    constexpr int smem = tc_smem_bytes<BN>();
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -775,6 +787,9 @@ static int pick_bn(int M, int N) {
     static const int forced = env_int("GB200_TC_BN", 0);        // tuning override (tools/bench_gemm.py)
     if (forced && N >= forced) return forced;
     const long long mt = cdiv(M, TC_BM);
+    static const int wide = env_int("GB200_TC_BN192", 1);
+    if (wide && N >= 192 && N % 192 == 0 && mt * cdiv(N, 128) > 2 * 148 && mt * (N / 192) <= 2 * 148)
+        return 192;      // one resident wave instead of two (the Q|K|V projection at C3: 232 CTAs, not 348)
     if (N >= 128 && mt * cdiv(N, 128) >= 148) return 128;
     if (N >= 64 && mt * cdiv(N, 64) >= 148) return 64;
     if (N >= 128) return mt * cdiv(N, 32) >= 148 ? 32 : 128;   // tiny problems: fewer, fatter CTAs
@@ -818,7 +833,7 @@ extern "C" int gb200_gemm_tc(int device, const float* A, int lda, int transA, co
     if (ksplit < 1) ksplit = 1;
     const bool a_mn = transA != 0;      // A stored [K, M]
     const bool b_mn = transB == 0;      // B stored [K, N]
-    const int bn = pick_bn(M, N);
+    int bn = pick_bn(M, N);
     TcArgs g;
     g.ep.C = C; g.ep.ldc = ldc; g.ep.sC = 0; g.ep.alpha = alpha; g.ep.bias = bias; g.ep.act = act; g.ep.Z = Zout;
     g.ep.ldz = ldz; g.ep.drop_p = drop_p; g.ep.seed = seed; g.ep.seed_off = rng_offset_ptr(); g.trace = g_tc_trace; g.ep.R = R; g.ep.ldr = ldr; g.ep.rscale = rscale;
@@ -836,16 +851,17 @@ extern "C" int gb200_gemm_tc(int device, const float* A, int lda, int transA, co
         GB_REQUIRE(workspace && workspace_bytes >= (size_t)g.ksplit * M * N * sizeof(float),
                    "gb200_gemm_tc: split-K workspace too small");
     GB_REQUIRE(!g.ep.hn_dk || (g.vec4 && g.ksplit == 1), "gb200_gemm_tc: fused head-norm needs the float4 epilogue");
+    static const int use_persistent = env_int("GB200_TC_PERSISTENT", 0);   // measured equal/slower in the full step
+    const bool persistent = use_persistent && g.ksplit == 1 && !g.ep.hn_dk;
+    if (bn == 192 && (persistent || g.ep.hn_dk)) bn = 128;
     CUtensorMap ma, mb;
     const CUtensorMapSwizzle SWK = CU_TENSOR_MAP_SWIZZLE_128B, SWMN = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
     bool ok = a_mn ? make_map(&ma, A, M, K, lda, 32, 32, SWMN) : make_map(&ma, A, K, M, lda, 32, TC_BM, SWK);
     ok = ok && (b_mn ? make_map(&mb, B, N, K, ldb, 32, 32, SWMN) : make_map(&mb, B, K, N, ldb, 32, bn, SWK));
     GB_REQUIRE(ok, "gb200_gemm_tc: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d lda=%d ldb=%d)", M, N, K, lda, ldb);
     cudaStream_t st = as_stream(stream);
-    static const int use_persistent = env_int("GB200_TC_PERSISTENT", 0);   // measured equal/slower in the full step
     static const int truncate = env_int("GB200_TC_TRUNCATE", 0);
     g.truncate = truncate;
-    const bool persistent = use_persistent && g.ksplit == 1 && !g.ep.hn_dk;
 #define TC_DISPATCH(BNV)                                                                          \
     do {                                                                                          \
         if (persistent) {                                                                         \
@@ -860,7 +876,12 @@ extern "C" int gb200_gemm_tc(int device, const float* A, int lda, int transA, co
             else launch_tc<BNV, true, true>(ma, mb, g, st);                                       \
         }                                                                                         \
     } while (0)
-    if (bn == 128) TC_DISPATCH(128);
+    if (bn == 192) {
+        if (!a_mn && !b_mn) launch_tc<192, false, false>(ma, mb, g, st);
+        else if (!a_mn && b_mn) launch_tc<192, false, true>(ma, mb, g, st);
+        else if (a_mn && !b_mn) launch_tc<192, true, false>(ma, mb, g, st);
+        else launch_tc<192, true, true>(ma, mb, g, st);
+    } else if (bn == 128) TC_DISPATCH(128);
     else if (bn == 64) TC_DISPATCH(64);
     else TC_DISPATCH(32);
 #undef TC_DISPATCH

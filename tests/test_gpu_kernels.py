@@ -116,6 +116,29 @@ def test_gemm_splitk_epilogue_is_deterministic(ksplit):
     assert torch.equal(outs[0], outs[1])
 
 
+@pytest.mark.parametrize("M,N,K", [(20000, 1, 128), (20000, 2, 130), (5000, 7, 33), (20000, 128, 1), (20000, 32, 2),
+                                   (1, 128, 20000), (32, 2, 20000), (3, 5, 9000), (30, 34, 9001)])
+@pytest.mark.parametrize("tA,tB", [(False, True), (False, False), (True, False), (True, True)])
+def test_gemm_degenerate_shapes(M, N, K, tA, tB):
+    """N = 1 output head, K = 2 grid columns, and their weight gradients (streaming kernels in gemm_simt.cu),
+    with the full epilogue; every layout must agree whether or not it takes a streaming path."""
+    A = rn(K, M) if tA else rn(M, K)
+    B = rn(N, K, seed=1) if tB else rn(K, N, seed=1)
+    bias, R = rn(N, seed=2), rn(M, N, seed=3)
+    C0 = rn(M, N, seed=4)
+    C = C0.clone()
+    Z = torch.empty(M, N, device=DEV)
+    GF.gemm(A, B, C, M, N, K, lda=A.shape[1], ldb=B.shape[1], ldc=N, transA=tA, transB=tB, alpha=0.5, bias=bias,
+            act=2, zout=Z, ldz=N, residual=R, ldr=N, rscale=-1.0, accumulate=True)
+    z = 0.5 * (A.double().t() if tA else A.double()) @ (B.double().t() if tB else B.double()) + bias.double()
+    ref = C0.double() + R.double() - torch.nn.functional.silu(z)
+    assert rel_l2(Z, z) < 5e-6 and rel_l2(C, ref) < 5e-6
+    C2 = C0.clone()
+    GF.gemm(A, B, C2, M, N, K, lda=A.shape[1], ldb=B.shape[1], ldc=N, transA=tA, transB=tB, alpha=0.5, bias=bias,
+            act=2, zout=Z, ldz=N, residual=R, ldr=N, rscale=-1.0, accumulate=True)
+    assert torch.equal(C, C2)                                # deterministic reductions
+
+
 def test_gemm_accumulate_and_offsets():
     M, N, K1, K2 = 50, 20, 12, 2
     x1, x2, W, b = rn(M, K1), rn(M, K2, seed=1), rn(N, K1 + K2, seed=2), rn(N, seed=3)
