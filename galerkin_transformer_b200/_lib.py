@@ -46,6 +46,10 @@ SIGNATURES = {
     "gb200_gemm_tc": (c_int, [c_int, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_int,
                               c_float, c_vp, c_int, c_vp, c_int, c_float, c_ull, c_vp, c_int, c_float, c_int,
                               c_int, c_vp, c_sz, c_vp]),
+    "gb200_gemm_tc_gated": (c_int, [c_int, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_int, c_float, c_float,
+                                    c_ull, c_float, c_vp, c_int, c_int, c_int, c_vp, c_sz, c_vp]),
+    "gb200_gemm_gated": (c_int, [c_int, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_int, c_float, c_float,
+                                    c_ull, c_float, c_vp, c_int, c_int, c_int, c_vp, c_sz, c_vp]),
     "gb200_gemm_tc_headnorm": (c_int, [c_int, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_int,
                                        c_int, c_int, c_int, c_float, c_vp, c_vp, c_vp]),
     "gb200_colsum_workspace_bytes": (c_sz, [c_ll, c_int]),

@@ -443,6 +443,9 @@ extern "C" int gb200_gemm(int device, const float* A, int lda, int transA, const
     g.ep.alpha = alpha; g.ep.bias = bias; g.ep.act = act; g.ep.Z = Zout; g.ep.ldz = ldz; g.ep.drop_p = drop_p;
     g.ep.seed = seed; g.ep.seed_off = rng_offset_ptr(); g.ep.R = R; g.ep.ldr = ldr; g.ep.rscale = rscale; g.ep.accumulate = accumulate;
     g.ep.hn_dk = 0; g.ep.hn_lo = g.ep.hn_hi = g.ep.hn_heads = 0; g.ep.hn_eps = 0.f; g.ep.hn_rstd[0] = g.ep.hn_rstd[1] = nullptr;
+    const GemmGate& gate = next_gemm_gate();
+    g.ep.G = gate.G; g.ep.ldg = gate.ldg; g.ep.gate = gate.act;
+    GB_REQUIRE(!gate.G || gate.act == ACT_RELU || gate.act == ACT_SILU, "gb200_gemm: unknown gate %d", gate.act);
     g.ws = workspace;
     g.vecA = ((uintptr_t)A % 16 == 0) && (lda % 4 == 0) && (strideA % 4 == 0);
     g.vecB = ((uintptr_t)B % 16 == 0) && (ldb % 4 == 0) && (strideB % 4 == 0);
@@ -488,6 +491,18 @@ extern "C" int gb200_gemm(int device, const float* A, int lda, int transA, const
         launch_pdl(splitk_reduce_kernel, blocks, 256, 0, st, g);
     }
     return check_launch("gb200_gemm", ksplit > 1 ? 2 : 1);
+}
+
+extern "C" int gb200_gemm_gated(int device, const float* A, int lda, int transA, const float* B, int ldb,
+                                int transB, float* C, int ldc, int M, int N, int K, float alpha, float drop_p,
+                                unsigned long long seed, float rscale, const float* gate, int ldg, int gate_act,
+                                int ksplit, float* workspace, size_t workspace_bytes, void* stream) {
+    GemmGate& gg = next_gemm_gate();
+    gg.G = gate; gg.ldg = ldg; gg.act = gate_act;
+    const int rc = gb200_gemm(device, A, lda, transA, B, ldb, transB, C, ldc, M, N, K, 1, 0, 0, 0, alpha, nullptr, ACT_NONE,
+                              nullptr, 0, drop_p, seed, nullptr, 0, rscale, 0, ksplit, workspace, workspace_bytes, stream);
+    gg.G = nullptr;
+    return rc;
 }
 
 extern "C" size_t gb200_colsum_workspace_bytes(long long M, int N) {

@@ -140,7 +140,9 @@ __device__ __forceinline__ float act_fast(float v) {
 
 // Coalesced float4 epilogue for one warp's 32 accumulator rows staged in shared memory.
 // Compile-time activation / dropout; residual, Z and accumulate are warp-uniform runtime switches.
-template <int ACT, bool DROP, bool HN = false>
+// GATE != 0 (host guarantees no residual / accumulate then): the rv registers carry the gate operand G instead and
+// v *= act'(G) before the dropout scale -- the elementwise backward between two Linear layers, fused.
+template <int ACT, bool DROP, bool HN = false, int GATE = 0>
 __device__ __forceinline__ void tc_epilogue_vec4(const TcArgs& g, const float* __restrict__ stage, int DS, int lane,
                                                  int rbase, int n0, int ncols, unsigned long long seed) {
     const GemmEpilogue& ep = g.ep;
@@ -158,7 +160,8 @@ __device__ __forceinline__ void tc_epilogue_vec4(const TcArgs& g, const float* _
         const int n = n0 + c;
         float4 bv = zero4;
         if (cv && ep.bias) bv = *reinterpret_cast<const float4*>(ep.bias + n);
-        const float* rp = hasR ? ep.R + (long long)rbase * ep.ldr + n : nullptr;
+        const float* rp = GATE ? ep.G + (long long)rbase * ep.ldg + n : (hasR ? ep.R + (long long)rbase * ep.ldr + n : nullptr);
+        const int ldr = GATE ? ep.ldg : ep.ldr;
         float* cp = ep.C + (long long)rbase * ep.ldc + n;
         float* zp = hasZ ? ep.Z + (long long)rbase * ep.ldz + n : nullptr;
 #pragma unroll 1
@@ -169,8 +172,8 @@ __device__ __forceinline__ void tc_epilogue_vec4(const TcArgs& g, const float* _
                 acc[i] = cv ? *reinterpret_cast<const float4*>(&stage[(r0 + i) * DS + c]) : zero4;
                 rv[i] = zero4;
                 if (cv && r0 + i < nrows) {
-                    if (hasR) rv[i] = *reinterpret_cast<const float4*>(rp + (long long)(r0 + i) * ep.ldr);
-                    if (accum) {
+                    if (GATE || hasR) rv[i] = *reinterpret_cast<const float4*>(rp + (long long)(r0 + i) * ldr);
+                    if (!GATE && accum) {
                         const float4 cvv = *reinterpret_cast<const float4*>(cp + (long long)(r0 + i) * ep.ldc);
                         rv[i].x += cvv.x; rv[i].y += cvv.y; rv[i].z += cvv.z; rv[i].w += cvv.w;
                     }
@@ -206,10 +209,18 @@ __device__ __forceinline__ void tc_epilogue_vec4(const TcArgs& g, const float* _
                 if (!cv) continue;
                 if (hasZ) *reinterpret_cast<float4*>(zp + (long long)(r0 + i) * ep.ldz) = z;
                 float4 v = make_float4(act_fast<ACT>(z.x), act_fast<ACT>(z.y), act_fast<ACT>(z.z), act_fast<ACT>(z.w));
+                if (GATE == ACT_RELU) {
+                    v.x = rv[i].x > 0.f ? v.x : 0.f; v.y = rv[i].y > 0.f ? v.y : 0.f;
+                    v.z = rv[i].z > 0.f ? v.z : 0.f; v.w = rv[i].w > 0.f ? v.w : 0.f;
+                } else if (GATE == ACT_SILU) {
+                    v.x *= act_grad(ACT_SILU, rv[i].x); v.y *= act_grad(ACT_SILU, rv[i].y);
+                    v.z *= act_grad(ACT_SILU, rv[i].z); v.w *= act_grad(ACT_SILU, rv[i].w);
+                }
                 if (DROP) {
                     const float4 ds = dropout_scale4(p, seed, (unsigned long long)(rbase + r0 + i) * g.N + n);
                     v.x *= ds.x; v.y *= ds.y; v.z *= ds.z; v.w *= ds.w;
                 }
+                if (GATE) rv[i] = zero4;
                 *reinterpret_cast<float4*>(cp + (long long)(r0 + i) * ep.ldc) =
                     make_float4(fmaf(rscale, v.x, rv[i].x), fmaf(rscale, v.y, rv[i].y), fmaf(rscale, v.z, rv[i].z),
                                 fmaf(rscale, v.w, rv[i].w));
@@ -413,6 +424,14 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
             const bool drop = ep.drop_p > 0.f;
             if (ep.hn_dk) {        // QKV projection with fused per-head LayerNorm (host guarantees act none, no dropout)
                 tc_epilogue_vec4<ACT_NONE, false, true>(g, stage, DS, lane, rbase, n0, ncols, seed);
+            } else if (ep.G) {     // gated backward GEMM (host guarantees act none, no residual / accumulate)
+                if (ep.gate == ACT_RELU) {
+                    if (drop) tc_epilogue_vec4<ACT_NONE, true, false, ACT_RELU>(g, stage, DS, lane, rbase, n0, ncols, seed);
+                    else tc_epilogue_vec4<ACT_NONE, false, false, ACT_RELU>(g, stage, DS, lane, rbase, n0, ncols, seed);
+                } else {
+                    if (drop) tc_epilogue_vec4<ACT_NONE, true, false, ACT_SILU>(g, stage, DS, lane, rbase, n0, ncols, seed);
+                    else tc_epilogue_vec4<ACT_NONE, false, false, ACT_SILU>(g, stage, DS, lane, rbase, n0, ncols, seed);
+                }
             } else if (ep.act == ACT_NONE) {
                 if (drop) tc_epilogue_vec4<ACT_NONE, true>(g, stage, DS, lane, rbase, n0, ncols, seed);
                 else tc_epilogue_vec4<ACT_NONE, false>(g, stage, DS, lane, rbase, n0, ncols, seed);
@@ -449,6 +468,10 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
                         float v = ep.alpha * acc[i] + bv;
                         if (ep.Z) ep.Z[(long long)row * ep.ldz + n] = v;
                         v = act_apply(ep.act, v);
+                        if (ep.G) {
+                            const float gv = ep.G[(long long)row * ep.ldg + n];
+                            v = ep.gate == ACT_RELU ? (gv > 0.f ? v : 0.f) : v * act_grad(ep.gate, gv);
+                        }
                         if (ep.drop_p > 0.f)
                             v *= dropout_scale(ep.drop_p, seed, (unsigned long long)row * g.N + n);
                         v = ep.R ? rv[i] + ep.rscale * v : ep.rscale * v;
@@ -838,6 +861,10 @@ extern "C" int gb200_gemm_tc(int device, const float* A, int lda, int transA, co
     g.ep.C = C; g.ep.ldc = ldc; g.ep.sC = 0; g.ep.alpha = alpha; g.ep.bias = bias; g.ep.act = act; g.ep.Z = Zout;
     g.ep.ldz = ldz; g.ep.drop_p = drop_p; g.ep.seed = seed; g.ep.seed_off = rng_offset_ptr(); g.trace = g_tc_trace; g.ep.R = R; g.ep.ldr = ldr; g.ep.rscale = rscale;
     g.ep.accumulate = accumulate;
+    const GemmGate& gate = next_gemm_gate();
+    g.ep.G = gate.G; g.ep.ldg = gate.ldg; g.ep.gate = gate.act;
+    GB_REQUIRE(!gate.G || ((gate.act == ACT_RELU || gate.act == ACT_SILU) && act == ACT_NONE && !g_hn.dk),
+               "gb200_gemm_tc: bad gate (act %d)", gate.act);
     g.ep.hn_dk = g_hn.dk; g.ep.hn_lo = g_hn.lo; g.ep.hn_hi = g_hn.hi; g.ep.hn_heads = g_hn.heads; g.ep.hn_eps = g_hn.eps;
     g.ep.hn_rstd[0] = g_hn.rstd[0]; g.ep.hn_rstd[1] = g_hn.rstd[1];
     g.M = M; g.N = N; g.K = K; g.ksplit = ksplit;
@@ -846,13 +873,14 @@ extern "C" int gb200_gemm_tc(int device, const float* A, int lda, int transA, co
     g.ws = workspace;
     auto al16 = [](const void* p) { return ((uintptr_t)p % 16) == 0; };
     g.vec4 = (N % 4 == 0) && al16(C) && (ldc % 4 == 0) && (!R || (al16(R) && ldr % 4 == 0)) &&
-             (!Zout || (al16(Zout) && ldz % 4 == 0)) && (!bias || al16(bias)) && (!workspace || al16(workspace));
+             (!Zout || (al16(Zout) && ldz % 4 == 0)) && (!bias || al16(bias)) && (!workspace || al16(workspace)) &&
+             (!gate.G || (al16(gate.G) && gate.ldg % 4 == 0 && !R && !accumulate));
     if (g.ksplit > 1)
         GB_REQUIRE(workspace && workspace_bytes >= (size_t)g.ksplit * M * N * sizeof(float),
                    "gb200_gemm_tc: split-K workspace too small");
     GB_REQUIRE(!g.ep.hn_dk || (g.vec4 && g.ksplit == 1), "gb200_gemm_tc: fused head-norm needs the float4 epilogue");
     static const int use_persistent = env_int("GB200_TC_PERSISTENT", 0);   // measured equal/slower in the full step
-    const bool persistent = use_persistent && g.ksplit == 1 && !g.ep.hn_dk;
+    const bool persistent = use_persistent && g.ksplit == 1 && !g.ep.hn_dk && !g.ep.G;
     if (bn == 192 && (persistent || g.ep.hn_dk)) bn = 128;
     CUtensorMap ma, mb;
     const CUtensorMapSwizzle SWK = CU_TENSOR_MAP_SWIZZLE_128B, SWMN = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
@@ -892,6 +920,18 @@ extern "C" int gb200_gemm_tc(int device, const float* A, int lda, int transA, co
         launch_pdl(tc_splitk_reduce_kernel, blocks, 256, 0, st, g);
     }
     return check_launch("gb200_gemm_tc", g.ksplit > 1 ? 2 : 1);
+}
+
+extern "C" int gb200_gemm_tc_gated(int device, const float* A, int lda, int transA, const float* B, int ldb, int transB,
+                                   float* C, int ldc, int M, int N, int K, float alpha, float drop_p,
+                                   unsigned long long seed, float rscale, const float* gate, int ldg, int gate_act,
+                                   int ksplit, float* workspace, size_t workspace_bytes, void* stream) {
+    GemmGate& gg = next_gemm_gate();
+    gg.G = gate; gg.ldg = ldg; gg.act = gate_act;
+    const int rc = gb200_gemm_tc(device, A, lda, transA, B, ldb, transB, C, ldc, M, N, K, alpha, nullptr, ACT_NONE, nullptr,
+                                 0, drop_p, seed, nullptr, 0, rscale, 0, ksplit, workspace, workspace_bytes, stream);
+    gg.G = nullptr;
+    return rc;
 }
 
 /* y = x W^T + b with per-head LayerNorm statistics fused into the epilogue: columns [col_lo, col_hi) of the output

@@ -4,6 +4,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "gemm_epilogue.cuh"
 
 namespace gb200 {
 
@@ -13,6 +14,11 @@ static std::atomic<unsigned long long> g_launches{0};
 static const unsigned long long* g_rng_offset = nullptr;
 
 const unsigned long long* rng_offset_ptr() { return g_rng_offset; }
+
+GemmGate& next_gemm_gate() {
+    static thread_local GemmGate g = {nullptr, 0, 0};
+    return g;
+}
 
 bool pdl_enabled() {
     static const bool on = [] {

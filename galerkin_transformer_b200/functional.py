@@ -125,8 +125,8 @@ def set_backward_streams(on):
 
 
 class _Fork:
-    """`with fork.side(i):` enqueues on side stream i (which first waits for everything enqueued on the launching
-    stream so far); `join()` makes the launching stream wait for the side work.  Outputs must be allocated BEFORE
+    """`with fork.side(i):` enqueues on side stream i (which first waits, on every entry, for everything enqueued on
+    the launching stream so far); `join()` makes the launching stream wait for the side work.  Outputs must be allocated BEFORE
     entering a side context (they then belong to the launching stream's allocator pool, and the join orders every
     later use after the side-stream writes); scratch allocated inside stays on the side stream."""
 
@@ -142,8 +142,8 @@ class _Fork:
         while len(pool) <= i:
             pool.append(torch.cuda.Stream(device=self.device))
         s = pool[i]
+        s.wait_stream(self.main)       # on EVERY entry: later side work may consume later launching-stream results
         if s not in self.used:
-            s.wait_stream(self.main)
             self.used.append(s)
         return torch.cuda.stream(s)
 
@@ -158,13 +158,26 @@ class _Fork:
 # ------------------------------------------------------------------------------------------
 def gemm(A, B, C, M, N, K, *, lda, ldb, ldc, transA=False, transB=False, alpha=1.0, bias=None, act=0,
          zout=None, ldz=0, drop_p=0.0, seed=0, residual=None, ldr=0, rscale=1.0, accumulate=False,
-         ksplit=None, a_off=0, b_off=0, c_off=0):
-    """C = R + rscale*drop(act(alpha*op(A).op(B)+bias)); offsets are in floats."""
+         ksplit=None, a_off=0, b_off=0, c_off=0, gate=None, ldg=0, gate_act=0):
+    """C = R + rscale*drop(act(alpha*op(A).op(B)+bias)); offsets are in floats.
+    gate (with gate_act relu|silu): C = rscale*drop((alpha*op(A).op(B)) * act'(gate)) -- no bias/act/residual."""
     lib = _lib.load()
     pa, pb = ptr(A) + 4 * a_off, ptr(B) + 4 * b_off
-    nbytes = 4.0 * (M * K + K * N + M * N * (1 + (residual is not None) + (zout is not None)))
+    nbytes = 4.0 * (M * K + K * N + M * N * (1 + (residual is not None) + (zout is not None) + (gate is not None)))
     lay = ("t" if transA else "n") + ("t" if transB else "n")
-    if _PRECISION == "tf32" and lib.gb200_gemm_tc_supported(pa, lda, pb, ldb, M, N, K):
+    use_tc = _PRECISION == "tf32" and lib.gb200_gemm_tc_supported(pa, lda, pb, ldb, M, N, K)
+    if gate is not None:
+        assert bias is None and act == 0 and zout is None and residual is None and not accumulate
+        if ksplit is None:
+            ksplit = lib.gb200_gemm_tc_suggest_ksplit(M, N, K) if use_tc else lib.gb200_gemm_suggest_ksplit(M, N, K, 1)
+        ws_bytes = ksplit * M * N * 4 if ksplit > 1 else 0
+        ws = workspace(ws_bytes, C)
+        fn = lib.gb200_gemm_tc_gated if use_tc else lib.gb200_gemm_gated
+        _launch(("gemm_tc_" if use_tc else "gemm_simt_") + lay, 2.0 * M * N * K, nbytes, fn, _dev(C), pa, lda, int(transA),
+                pb, ldb, int(transB), ptr(C) + 4 * c_off, ldc, M, N, K, alpha, drop_p, seed, rscale, ptr(gate), ldg,
+                gate_act, ksplit, ptr(ws), ws_bytes, stream_of(C))
+        return
+    if use_tc:
         if ksplit is None:
             ksplit = lib.gb200_gemm_tc_suggest_ksplit(M, N, K)
         ws_bytes = ksplit * M * N * 4 if ksplit > 1 else 0
@@ -296,6 +309,103 @@ class _LinearFn(torch.autograd.Function):
         fork.join()
         dres = dy if (has_res and ctx.needs_input_grad[3]) else None
         return dx, dw, db, dres, None, None, None, None
+
+
+class _MLP2Fn(torch.autograd.Function):
+    """y = [x +] rscale * drop_p2( drop_p1(act(x W1^T + b1)) W2^T + b2 )  -- FeedForward (libs/layers.py:979-987) with
+    the encoder's residual + dropout2 (libs/model.py:132), and the regressor head Linear-act-Linear
+    (libs/model.py:595-600, 629).  One autograd node, so backward is three launches on the critical path:
+        g2 = dy * mask2 * rscale            (skipped when p2 = 0 and rscale = 1)
+        g1 = (g2 W2) * act'(z1) * mask1     (gated GEMM epilogue: no elementwise pass between the layers)
+        dx = dy + g1 W1                     (the shortcut's gradient rides in the last GEMM's epilogue)
+    while dW2, dW1, db1 (and db2) run on the side streams."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, act, p1, seed1, p2, seed2, rscale, shortcut):
+        require_cuda_f32(x, w1, b1, w2, b2)
+        M, K = x.shape
+        N1, N2 = w1.shape[0], w2.shape[0]
+        h = torch.empty((M, N1), dtype=torch.float32, device=x.device)
+        need_grad = x.requires_grad or w1.requires_grad or w2.requires_grad
+        z1 = torch.empty_like(h) if (act == ACT["silu"] and need_grad) else None
+        gemm(x, w1, h, M, N1, K, lda=K, ldb=K, ldc=N1, transB=True, bias=b1, act=act, zout=z1, ldz=N1, drop_p=p1,
+             seed=seed1)
+        y = torch.empty((M, N2), dtype=torch.float32, device=x.device)
+        gemm(h, w2, y, M, N2, N1, lda=N1, ldb=N1, ldc=N2, transB=True, bias=b2, drop_p=p2, seed=seed2,
+             residual=x if shortcut else None, ldr=K, rscale=rscale)
+        ctx.save_for_backward(x, w1, w2, h, z1)
+        ctx.cfg = (act, p1, seed1, p2, seed2, rscale, shortcut, b1 is not None, b2 is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w1, w2, h, z1 = ctx.saved_tensors
+        act, p1, seed1, p2, seed2, rscale, shortcut, has_b1, has_b2 = ctx.cfg
+        dy = dy.contiguous()
+        M, K = x.shape
+        N1, N2 = w1.shape[0], w2.shape[0]
+        lib = _lib.load()
+        dx = dw1 = db1 = dw2 = db2 = None
+        want_db2 = has_b2 and ctx.needs_input_grad[4]
+        fork = _Fork(dy)
+        if p2 > 0.0 or rscale != 1.0:
+            if want_db2:
+                g2 = torch.empty_like(dy)
+                db2 = torch.empty(N2, dtype=torch.float32, device=dy.device)
+                wsb = lib.gb200_epilogue_bwd_bias_workspace_bytes(M, N2)
+                ws = workspace(wsb, dy)
+                _launch("epilogue_bwd_bias", 5.0 * M * N2, 8.0 * M * N2, lib.gb200_epilogue_bwd_bias, _dev(dy), ptr(dy),
+                        N2, None, N2, None, N2, ptr(g2), N2, M, N2, 0, rscale, p2, seed2, ptr(db2), ptr(ws), wsb,
+                        stream_of(dy))
+            else:
+                g2 = epilogue_bwd(dy, M, N2, rscale=rscale, drop_p=p2, seed=seed2)
+        else:
+            g2 = dy
+            if want_db2:
+                db2 = torch.empty(N2, dtype=torch.float32, device=dy.device)
+                with fork.side(1):
+                    colsum(g2, M, N2, N2, db2)
+        if ctx.needs_input_grad[3]:
+            dw2 = torch.empty_like(w2)
+            with fork.side(0):
+                gemm(g2, h, dw2, N2, N1, M, lda=N2, ldb=N1, ldc=N1, transA=True)
+        # g1 = (g2 W2) * act'(.) * mask1: ReLU gates on the stored (post-dropout) output, SiLU on the pre-activation
+        g1 = torch.empty_like(h)
+        if act == ACT["none"] and p1 == 0.0:
+            gemm(g2, w2, g1, M, N1, N2, lda=N2, ldb=N1, ldc=N1)
+        elif act == ACT["none"]:
+            # dropout only: gate on "kept" via a ReLU gate is wrong for negative values -> plain GEMM + mask pass
+            gemm(g2, w2, g1, M, N1, N2, lda=N2, ldb=N1, ldc=N1)
+            g1 = epilogue_bwd(g1, M, N1, drop_p=p1, seed=seed1)
+        else:
+            gemm(g2, w2, g1, M, N1, N2, lda=N2, ldb=N1, ldc=N1, drop_p=p1, seed=seed1,
+                 gate=h if act == ACT["relu"] else z1, ldg=N1, gate_act=act)
+        if ctx.needs_input_grad[1]:
+            dw1 = torch.empty_like(w1)
+            with fork.side(0):
+                gemm(g1, x, dw1, N1, K, M, lda=N1, ldb=K, ldc=K, transA=True)
+        if has_b1 and ctx.needs_input_grad[2]:
+            db1 = torch.empty(N1, dtype=torch.float32, device=dy.device)
+            with fork.side(1):
+                colsum(g1, M, N1, N1, db1)
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            gemm(g1, w1, dx, M, K, N1, lda=N1, ldb=K, ldc=K, residual=dy if shortcut else None, ldr=N2)
+        fork.join()
+        return dx, dw1, db1, dw2, db2, None, None, None, None, None, None, None
+
+
+def mlp2(x, w1, b1, w2, b2, *, act="relu", drop_p1=0.0, drop_p2=0.0, rscale=1.0, shortcut=False):
+    """Linear -> act -> dropout -> Linear [-> dropout -> rscale -> + x]; any leading shape."""
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1]).contiguous()
+    if shortcut:
+        assert w2.shape[0] == x2.shape[1]
+    seed1 = next_seed() if drop_p1 > 0.0 else 0
+    seed2 = next_seed() if drop_p2 > 0.0 else 0
+    y = _MLP2Fn.apply(x2, w1, b1, w2, b2, ACT[act], float(drop_p1), seed1, float(drop_p2), seed2, float(rscale),
+                      bool(shortcut))
+    return y.reshape(*lead, w2.shape[0])
 
 
 def linear(x, weight, bias=None, *, act="none", residual=None, rscale=1.0, drop_p=0.0):
@@ -521,6 +631,12 @@ class _LinearAttentionFn(torch.autograd.Function):
         G = torch.empty((B, H, d, d), dtype=torch.float32, device=query.device)
         xty_work = (2.0 * B * H * n * d * d, 4.0 * (T * dm + T * p + T * H * d))
         xm_work = (2.0 * B * H * n * d * d, 4.0 * (2 * T * dm + T * p))
+        dqkv = torch.empty((T, 3 * dm), dtype=torch.float32, device=query.device)
+        # dQ~ = dO A^T needs nothing from the G chain: side stream 0, concurrent with the contraction below
+        fork = _Fork(dout)
+        with fork.side(0):
+            _launch("attn_xm", *xm_work, lib.gb200_attn_xm, dev, do_op, ptr(pos), ptr(A), 1, B, H, n, dk, p, ptr(dqkv),
+                    3 * dm, 0, 0, 1.0, tc, stream_of(query))
         nsplit = lib.gb200_attn_suggest_nsplit(B, H, n)
         ws_bytes = lib.gb200_attn_xty_workspace_bytes(B, H, d, nsplit)
         ws = workspace(ws_bytes, qkv)
@@ -538,14 +654,13 @@ class _LinearAttentionFn(torch.autograd.Function):
                 check(lib.gb200_philox_scale(dev, ptr(drop), drop.numel(), mask_p, mask_seed, st), "gb200_philox_scale")
                 G = G * drop
             G = G.contiguous()
-        dqkv = torch.empty((T, 3 * dm), dtype=torch.float32, device=query.device)
-        # dQ~ = dO A^T ; dV~ = K~ G ; dK~ = V~ G^T   (position columns carry no gradient)
-        _launch("attn_xm", *xm_work, lib.gb200_attn_xm, dev, do_op, ptr(pos), ptr(A), 1, B, H, n, dk, p, ptr(dqkv),
-                3 * dm, 0, 0, 1.0, tc, st)
-        _launch("attn_xm", *xm_work, lib.gb200_attn_xm, dev, ops[1], ptr(pos), ptr(G), 0, B, H, n, dk, p, ptr(dqkv),
-                3 * dm, 2 * dm, 0, 1.0, tc, st)
+        # dV~ = K~ G (side stream 1) ; dK~ = V~ G^T   (position columns carry no gradient)
+        with fork.side(1):
+            _launch("attn_xm", *xm_work, lib.gb200_attn_xm, dev, ops[1], ptr(pos), ptr(G), 0, B, H, n, dk, p, ptr(dqkv),
+                    3 * dm, 2 * dm, 0, 1.0, tc, stream_of(query))
         _launch("attn_xm", *xm_work, lib.gb200_attn_xm, dev, ops[2], ptr(pos), ptr(G), 1, B, H, n, dk, p, ptr(dqkv),
                 3 * dm, dm, 0, 1.0, tc, st)
+        fork.join()
         return _LinearAttentionFn._finish_backward(ctx, dqkv, blocks, rstd, qkv, g1, g2, query, key, value, wqkv, flat,
                                                    H, dk, T, dm, self_attn, dev, st)
 

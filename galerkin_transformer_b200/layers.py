@@ -178,6 +178,9 @@ class FeedForward(nn.Module):
 
     def forward(self, x, residual=None, rscale=1.0, out_drop_p=0.0):
         p = self.dropout.p if self.training else 0.0
+        if residual is None or residual is x:     # one autograd node: gated backward GEMM, shortcut gradient fused
+            return GF.mlp2(x, self.lr1.weight, self.lr1.bias, self.lr2.weight, self.lr2.bias, act=self.act_name,
+                           drop_p1=p, drop_p2=out_drop_p, rscale=rscale, shortcut=residual is not None)
         h = GF.linear(x, self.lr1.weight, self.lr1.bias, act=self.act_name, drop_p=p)
         return GF.linear(h, self.lr2.weight, self.lr2.bias, residual=residual, rscale=rscale,
                          drop_p=out_drop_p)

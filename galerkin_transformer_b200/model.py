@@ -179,8 +179,7 @@ class SpectralRegressor(nn.Module):
             if self.return_latent:
                 x_latent.append(x.contiguous())
         r0, r2 = self.regressor[0], self.regressor[2]
-        x = GF.linear(x, r0.weight, r0.bias, act=_act_name(self.regressor[1]))
-        x = GF.linear(x, r2.weight, r2.bias)
+        x = GF.mlp2(x, r0.weight, r0.bias, r2.weight, r2.bias, act=_act_name(self.regressor[1]))
         if self.normalizer:
             x = self.normalizer.inverse_transform(x)
         if self.return_freq or self.return_latent:

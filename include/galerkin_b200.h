@@ -83,6 +83,21 @@ int gb200_gemm_tc(int device, const float* A, int lda, int transA, const float* 
                   float rscale, int accumulate, int ksplit, float* workspace, size_t workspace_bytes,
                   void* stream);
 
+/* Gated GEMM: C = rscale * dropout_p( (alpha * op(A).op(B)) * act'(gate) ), gate_act = GB200_ACT_RELU (keep where
+ * gate > 0; `gate` may be the stored post-activation/post-dropout output) or GB200_ACT_SILU (times silu'(gate), `gate`
+ * = stored pre-activation).  With (seed, drop_p, rscale) of the forward layer this is "input gradient of layer i+1,
+ * pushed through the activation and dropout of layer i" in one launch -- the elementwise backward between
+ * lr2 and lr1 of FeedForward (libs/layers.py:980-986) and between `out` and the hidden layer of the regressor
+ * (libs/model.py:629).  gb200_gemm_gated is the exact-fp32 / odd-shape path (N = 1 head: a rank-1 streaming kernel). */
+int gb200_gemm_tc_gated(int device, const float* A, int lda, int transA, const float* B, int ldb, int transB,
+                        float* C, int ldc, int M, int N, int K, float alpha, float drop_p, unsigned long long seed,
+                        float rscale, const float* gate, int ldg, int gate_act, int ksplit, float* workspace,
+                        size_t workspace_bytes, void* stream);
+int gb200_gemm_gated(int device, const float* A, int lda, int transA, const float* B, int ldb, int transB,
+                     float* C, int ldc, int M, int N, int K, float alpha, float drop_p, unsigned long long seed,
+                     float rscale, const float* gate, int ldg, int gate_act, int ksplit, float* workspace,
+                     size_t workspace_bytes, void* stream);
+
 /* C = A W^T + bias on the tensor cores with per-head LayerNorm statistics fused into the epilogue: output columns
  * [col_lo, col_hi) -- one or two operand blocks of heads*dk columns, e.g. K and V of the packed Q|K|V projection --
  * are replaced by (y - mean) * rstd per (row, head); rstd goes to rstd_a / rstd_b (rows, heads).

@@ -99,6 +99,74 @@ def test_linear_autograd_tensor_cores(act):
         assert rel_l2(g, r) < 5e-3
 
 
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("act,p1,p2,shortcut,dims", [
+    ("relu", 0.0, 0.0, True, (1849, 128, 256, 128)), ("relu", 0.2, 0.1, True, (1849, 128, 256, 128)),
+    ("silu", 0.2, 0.1, True, (777, 64, 136, 64)), ("silu", 0.0, 0.0, False, (5000, 32, 128, 1)),
+    ("relu", 0.3, 0.0, False, (5000, 32, 128, 3)), ("none", 0.2, 0.0, False, (300, 24, 40, 24))])
+def test_mlp2_matches_two_linear_nodes(precision, act, p1, p2, shortcut, dims):
+    """The fused Linear-act-dropout-Linear node (gated backward GEMM, shortcut gradient in the last GEMM's epilogue,
+    weight gradients on side streams) against the same computation as two `linear` nodes with the same Philox
+    keys: same forward bits, gradients to round-off."""
+    GF.set_precision(precision)
+    M, K, N1, N2 = dims
+    x = rn(M, K).requires_grad_(True)
+    W1 = (0.2 * rn(N1, K, seed=1)).requires_grad_(True)
+    b1 = rn(N1, seed=2).requires_grad_(True)
+    W2 = (0.2 * rn(N2, N1, seed=3)).requires_grad_(True)
+    b2 = rn(N2, seed=4).requires_grad_(True)
+    cot = rn(M, N2, seed=5)
+    leaves = [x, W1, b1, W2, b2]
+    torch.manual_seed(11); GF._seed_counter = 0
+    h = GF.linear(x, W1, b1, act=act, drop_p=p1)
+    ya = GF.linear(h, W2, b2, residual=x if shortcut else None, rscale=-1.0 if shortcut else 1.0, drop_p=p2)
+    ga = torch.autograd.grad((ya * cot).sum(), leaves)
+    torch.manual_seed(11); GF._seed_counter = 0
+    yb = GF.mlp2(x, W1, b1, W2, b2, act=act, drop_p1=p1, drop_p2=p2, rscale=-1.0 if shortcut else 1.0,
+                 shortcut=shortcut)
+    gb = torch.autograd.grad((yb * cot).sum(), leaves)
+    assert rel_l2(yb, ya) < 1e-6
+    for a_, b_ in zip(gb, ga):
+        assert rel_l2(b_, a_) < 2e-5, rel_l2(b_, a_)
+    if p1 == 0.0 and p2 == 0.0 and precision == "fp32":      # and against plain fp64 math
+        xd, W1d, b1d, W2d, b2d = [t.detach().double().requires_grad_(True) for t in leaves]
+        z = xd @ W1d.t() + b1d
+        hd = {"none": z, "relu": torch.relu(z), "silu": torch.nn.functional.silu(z)}[act]
+        yd = hd @ W2d.t() + b2d
+        yd = xd - yd if shortcut else yd
+        gd = torch.autograd.grad((yd * cot.double()).sum(), [xd, W1d, b1d, W2d, b2d])
+        assert rel_l2(yb, yd) < TOL
+        for a_, b_ in zip(gb, gd):
+            assert rel_l2(a_, b_) < 1e-5
+
+
+@pytest.mark.parametrize("gate_act", ["relu", "silu"])
+@pytest.mark.parametrize("M,N,K,tc", [(1000, 256, 128, True), (14792, 256, 128, True), (300, 40, 24, False),
+                                      (5000, 128, 1, False), (130, 72, 33, True)])
+def test_gated_gemm(gate_act, M, N, K, tc):
+    """C = rscale * dropout((A.B) * act'(G)): tcgen05 float4 / scalar epilogues, SIMT and the rank-1 streaming kernel."""
+    GF.set_precision("tf32" if tc else "fp32")
+    Ks = -(-K // 4) * 4 if tc else K
+    A = rn(M, Ks)[:, :K]
+    B = rn(K, N, seed=1)
+    G = rn(M, N, seed=2)
+    C = torch.empty(M, N, device=DEV)
+    p, seed = 0.25, 1234
+    GF.gemm(A, B, C, M, N, K, lda=A.stride(0), ldb=N, ldc=N, drop_p=p, seed=seed, rscale=-0.5, gate=G, ldg=N,
+            gate_act=GF.ACT[gate_act])
+    mask = torch.ones(M, N, device=DEV)
+    _lib.check(_lib.load().gb200_philox_scale(0, mask.data_ptr(), M * N, p, seed,
+                                              torch.cuda.current_stream().cuda_stream), "philox")
+    d = G.double()
+    if gate_act == "relu":
+        gd = (d > 0).double()
+    else:
+        s = torch.sigmoid(d)
+        gd = s * (1 + d * (1 - s))
+    ref = -0.5 * (A.double() @ B.double()) * gd * mask.double()
+    assert rel_l2(C, ref) < (TF32_TOL if tc else 5e-6), rel_l2(C, ref)
+
+
 @pytest.mark.parametrize("ksplit", [1, 3, 16])
 def test_gemm_splitk_epilogue_is_deterministic(ksplit):
     M, N, K = 96, 80, 4000
