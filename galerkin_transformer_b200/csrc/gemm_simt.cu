@@ -170,6 +170,26 @@ __global__ void __launch_bounds__(256) gemm_thin_k_kernel(SkinnyArgs g) {
     }
 }
 
+// float4 variant: four consecutive output columns per thread (N % 4 == 0, every [M,N] operand 16-byte aligned)
+template <int KMAX>
+__global__ void __launch_bounds__(256) gemm_thin_k_vec4_kernel(SkinnyArgs g) {
+    pdl_enter();
+    const unsigned nq = (unsigned)g.N / 4u, total = (unsigned)g.M * nq;
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int m = (int)(e / nq), n = (int)(e % nq) * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+            if (k < g.K) {
+                const float a = g.A[m * g.sam + k * g.sak];
+                const float* b = g.B + k * g.sbk + n * g.sbn;
+                acc.x = fmaf(a, b[0], acc.x); acc.y = fmaf(a, b[g.sbn], acc.y);
+                acc.z = fmaf(a, b[2 * g.sbn], acc.z); acc.w = fmaf(a, b[3 * g.sbn], acc.w);
+            }
+        g.ep.store4(m, n, g.N, acc);
+    }
+}
+
 // (2) tiny output width (N <= 8), row-major A: one warp per output row, lanes stride the contraction
 template <int NMAX>
 __global__ void __launch_bounds__(256) gemm_thin_n_kernel(SkinnyArgs g) {
@@ -192,6 +212,46 @@ __global__ void __launch_bounds__(256) gemm_thin_n_kernel(SkinnyArgs g) {
             const float s = warp_sum(acc[n]);
             if (lane == n && n < g.N) g.ep.store(0, m, n, g.M, g.N, s);
         }
+    }
+}
+
+// N = 1..2 with K % 4 == 0, 16-byte aligned rows and k-contiguous B (transB): float4 along the contraction, four
+// rows of A in flight per warp
+template <int NMAX>
+__global__ void __launch_bounds__(256) gemm_thin_n_vec4_kernel(SkinnyArgs g) {
+    pdl_enter();
+    constexpr int RU = 4;
+    const int lane = threadIdx.x % 32;
+    const int wglobal = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, nwarps = gridDim.x * (blockDim.x / 32);
+    const int kq = g.K / 4;
+    for (int m0 = wglobal * RU; m0 < g.M; m0 += nwarps * RU) {
+        float acc[RU][NMAX];
+#pragma unroll
+        for (int r = 0; r < RU; ++r)
+#pragma unroll
+            for (int n = 0; n < NMAX; ++n) acc[r][n] = 0.f;
+        for (int q = lane; q < kq; q += 32) {
+            float4 av[RU];
+#pragma unroll
+            for (int r = 0; r < RU; ++r)
+                av[r] = m0 + r < g.M ? *reinterpret_cast<const float4*>(g.A + (long long)(m0 + r) * g.sam + 4 * q)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int n = 0; n < NMAX; ++n)
+                if (n < g.N) {
+                    const float4 bv = *reinterpret_cast<const float4*>(g.B + n * g.sbn + 4 * q);
+#pragma unroll
+                    for (int r = 0; r < RU; ++r)
+                        acc[r][n] = fmaf(av[r].x, bv.x, fmaf(av[r].y, bv.y, fmaf(av[r].z, bv.z, fmaf(av[r].w, bv.w, acc[r][n]))));
+                }
+        }
+#pragma unroll
+        for (int r = 0; r < RU; ++r)
+#pragma unroll
+            for (int n = 0; n < NMAX; ++n) {
+                const float s = warp_sum(acc[r][n]);
+                if (lane == r * NMAX + n && n < g.N && m0 + r < g.M) g.ep.store(0, m0 + r, n, g.M, g.N, s);
+            }
     }
 }
 
@@ -251,6 +311,51 @@ __global__ void __launch_bounds__(256) gemm_tall_partial_kernel(SkinnyArgs g) {
             if (e < E) g.ws[(long long)blockIdx.x * E + e] = s;
         }
         __syncthreads();
+    }
+}
+// float4 along n (N % 4 == 0, B rows 16-byte aligned, M*N/4 <= 256): one B row = N/4 lanes, 256/(M*N/4) k-rows per pass
+__global__ void __launch_bounds__(256) gemm_tall_partial_vec4_kernel(SkinnyArgs g) {
+    pdl_enter();
+    __shared__ float4 red[256];
+    const int E4 = g.M * g.N / 4;
+    const int KP = 256 / E4;
+    const int kk = threadIdx.x / E4, e4 = threadIdx.x % E4;
+    const bool active = kk < KP;
+    const int m = (e4 * 4) / g.N, n = (e4 * 4) % g.N;
+    const int kbeg = blockIdx.x * g.kchunk, kend = min(g.K, kbeg + g.kchunk);
+    const float* ap = g.A + m * g.sam;
+    const float* bp = g.B + n;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) {
+        int k = kbeg + kk;
+        for (; k + 7 * KP < kend; k += 8 * KP) {      // eight independent k-rows per thread in flight
+            float av[8]; float4 bv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                av[u] = ap[(long long)(k + u * KP) * g.sak];
+                bv[u] = *reinterpret_cast<const float4*>(bp + (long long)(k + u * KP) * g.sbk);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                acc.x = fmaf(av[u], bv[u].x, acc.x); acc.y = fmaf(av[u], bv[u].y, acc.y);
+                acc.z = fmaf(av[u], bv[u].z, acc.z); acc.w = fmaf(av[u], bv[u].w, acc.w);
+            }
+        }
+        for (; k < kend; k += KP) {
+            const float a = ap[(long long)k * g.sak];
+            const float4 b = *reinterpret_cast<const float4*>(bp + (long long)k * g.sbk);
+            acc.x = fmaf(a, b.x, acc.x); acc.y = fmaf(a, b.y, acc.y); acc.z = fmaf(a, b.z, acc.z); acc.w = fmaf(a, b.w, acc.w);
+        }
+    }
+    red[threadIdx.x] = active ? acc : make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    if (kk == 0) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < KP; ++q) {
+            const float4 t = red[q * E4 + e4];
+            s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+        }
+        *reinterpret_cast<float4*>(g.ws + (long long)blockIdx.x * (E4 * 4) + e4 * 4) = s;
     }
 }
 __global__ void gemm_tall_final_kernel(SkinnyArgs g) {
@@ -461,9 +566,27 @@ extern "C" int gb200_gemm(int device, const float* A, int lda, int transA, const
         s.ksplit = ksplit;
         s.kchunk = cdiv(K > 0 ? K : 1, ksplit);
         const long long total = (long long)M * N;
+        auto al16 = [](const void* p) { return ((uintptr_t)p % 16) == 0; };
+        const GemmEpilogue& e = g.ep;
+        const bool out4 = N % 4 == 0 && al16(C) && ldc % 4 == 0 && (!e.bias || al16(e.bias)) &&
+                          (!e.Z || (al16(e.Z) && ldz % 4 == 0)) && (!e.R || (al16(e.R) && ldr % 4 == 0)) &&
+                          (!e.G || (al16(e.G) && e.ldg % 4 == 0));
+        if (K <= 8 && total < (1ll << 31) && out4) {
+            const long long quads = total / 4;
+            const int blocks = (int)(quads / 256 + 1 < 148 * 16 ? quads / 256 + 1 : 148 * 16);
+            if (K <= 2) launch_pdl(gemm_thin_k_vec4_kernel<2>, blocks, 256, 0, st, s);
+            else launch_pdl(gemm_thin_k_vec4_kernel<8>, blocks, 256, 0, st, s);
+            return check_launch("gb200_gemm(thin K, float4)", 1);
+        }
         if (K <= 8 && total < (1ll << 31)) {
             launch_pdl(gemm_thin_k_kernel, (int)(total / 256 + 1 < 148 * 16 ? total / 256 + 1 : 148 * 16), 256, 0, st, s);
             return check_launch("gb200_gemm(thin K)", 1);
+        }
+        if (N <= 2 && !transA && transB && M >= 1024 && K % 4 == 0 && al16(A) && al16(B) && lda % 4 == 0 && ldb % 4 == 0) {
+            const int blocks = cdiv(M, 32) < 148 * 16 ? cdiv(M, 32) : 148 * 16;
+            if (N == 1) launch_pdl(gemm_thin_n_vec4_kernel<1>, blocks, 256, 0, st, s);
+            else launch_pdl(gemm_thin_n_vec4_kernel<2>, blocks, 256, 0, st, s);
+            return check_launch("gb200_gemm(thin N, float4)", 1);
         }
         if (N <= 8 && !transA && M >= 1024) {
             const int blocks = cdiv(M, 8) < 148 * 16 ? cdiv(M, 8) : 148 * 16;
@@ -473,7 +596,10 @@ extern "C" int gb200_gemm(int device, const float* A, int lda, int transA, const
         }
         if (transA && !transB && total <= 1024 && ksplit > 1) {
             s.ksplit = cdiv(K, s.kchunk);
-            launch_pdl(gemm_tall_partial_kernel, s.ksplit, 256, 0, st, s);
+            if (N % 4 == 0 && total / 4 <= 256 && al16(B) && ldb % 4 == 0 && al16(workspace))
+                launch_pdl(gemm_tall_partial_vec4_kernel, s.ksplit, 256, 0, st, s);
+            else
+                launch_pdl(gemm_tall_partial_kernel, s.ksplit, 256, 0, st, s);
             launch_pdl(gemm_tall_final_kernel, cdiv(total, 32), dim3(32, 32), 0, st, s);
             return check_launch("gb200_gemm(tall)", 2);
         }

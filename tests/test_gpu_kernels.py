@@ -185,7 +185,7 @@ def test_gemm_splitk_epilogue_is_deterministic(ksplit):
 
 
 @pytest.mark.parametrize("M,N,K", [(20000, 1, 128), (20000, 2, 130), (5000, 7, 33), (20000, 128, 1), (20000, 32, 2),
-                                   (1, 128, 20000), (32, 2, 20000), (3, 5, 9000), (30, 34, 9001)])
+                                   (1, 128, 20000), (4, 64, 20000), (32, 2, 20000), (3, 5, 9000), (30, 34, 9001)])
 @pytest.mark.parametrize("tA,tB", [(False, True), (False, False), (True, False), (True, True)])
 def test_gemm_degenerate_shapes(M, N, K, tA, tB):
     """N = 1 output head, K = 2 grid columns, and their weight gradients (streaming kernels in gemm_simt.cu),
