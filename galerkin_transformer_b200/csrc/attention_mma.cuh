@@ -119,7 +119,7 @@ __device__ __forceinline__ void stage_aug(float* __restrict__ S, const HeadOpera
 
 // ---- xty: P[i][j] = sum_t L~[t][i] R~[t][j];  MT x NT tiles of 16 x 8, i < 16*MT, j < 8*NT --------------
 template <int MT, int NT>
-__global__ void __launch_bounds__(256, 3) xty_mma_kernel(HeadOperand L, HeadOperand R, const float* __restrict__ pos,
+__global__ void __launch_bounds__(256, 4) xty_mma_kernel(HeadOperand L, HeadOperand R, const float* __restrict__ pos,
                                                       int p, int dk, int H, int n, int nsplit, int chunk,
                                                       float* __restrict__ part) {
     pdl_enter();
