@@ -426,7 +426,10 @@ def main():
                         traffic=(traffic or {}).get("dram_bytes_per_launch"), traffic_note=(traffic or {}).get("note"),
                         alg_bytes_per_launch=top["alg_bytes_per_launch"], alg_flops_per_launch=top["alg_flops_per_launch"],
                         alg_tflops=top["alg_tflops"], tensor_frac_of_dense_tf32=round(top["alg_tflops"] / tf32_peak, 4),
-                        share_of_step=round(top["ms_per_step"] / ms_per_step, 4), gemm_layouts=layouts,
+                        share_of_step=round(top["ms_per_step"] / ms_per_step, 4),
+                        share_note="serial per-launch time / timed step; in the timed step the weight-gradient launches "
+                                   "run on side streams concurrently, so shares can sum past 1",
+                        gemm_layouts=layouts,
                         peak_source=f"MEASURED_PEAKS.json ({peaks['source']}); tensor peak = sustained bf16 / 2 "
                                     "(dense TF32)",
                         timing=f"CUDA events around every launch on the launching stream, {prof_steps}-step eager "
