@@ -71,6 +71,8 @@ SIGNATURES = {
     "gb200_attn_xty_workspace_bytes": (c_sz, [c_int] * 4),
     "gb200_attn_xty": (c_int, [c_int, _HOP, _HOP, c_vp, c_int, c_int, c_int, c_int, c_int, c_float, c_vp, c_float,
                                c_ull, c_vp, c_int, c_vp, c_sz, c_int, c_vp]),
+    "gb200_interp_bilinear_fwd": (c_int, [c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp]),
+    "gb200_interp_bilinear_bwd": (c_int, [c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp]),
     "gb200_philox_scale": (c_int, [c_int, c_vp, c_ll, c_float, c_ull, c_vp]),
     "gb200_attn_xm": (c_int, [c_int, _HOP, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp,
                               c_int, c_int, c_int, c_float, c_int, c_vp]),

@@ -1,0 +1,157 @@
+// Bilinear resize of channel-last grids, align_corners = True (the interpolation steps of the reference's
+// Interp2dEncoder / Interp2dUpsample scalers: libs/layers.py:431-512, 624-670 call F.interpolate(mode='bilinear',
+// align_corners=True) on (B, C, H, W); here the grid stays (B, H, W, C) in memory).
+//
+//   src_y = oy * (Hin - 1) / (Hout - 1),  y0 = floor(src_y), y1 = min(y0 + 1, Hin - 1), ly = src_y - y0
+//   out[b, oy, ox, :] = (1-ly) (1-lx) in[y0,x0] + (1-ly) lx in[y0,x1] + ly (1-lx) in[y1,x0] + ly lx in[y1,x1]
+//
+// Both directions are pure streaming passes: one thread per (pixel, 4 channels), float4 memory operations.  The
+// backward is a GATHER over the few output pixels whose stencil touches an input pixel (no atomics: deterministic).
+#include "common.cuh"
+
+namespace gb200 {
+
+struct InterpArgs {
+    const float* in; float* out;
+    int B, Hin, Win, Hout, Wout, C;
+    float sy, sx;            // (in - 1) / (out - 1), or 0 when out == 1
+};
+
+__device__ __forceinline__ void src_index(float scale, int dst, int nin, int& i0, int& i1, float& l) {
+    const float s = scale * dst;
+    i0 = min((int)s, nin - 1);
+    i1 = i0 + (i0 < nin - 1 ? 1 : 0);
+    l = s - (float)i0;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) interp_fwd_kernel(InterpArgs a) {
+    pdl_enter();
+    const int cq = VEC ? a.C / 4 : a.C;
+    const long long total = (long long)a.B * a.Hout * a.Wout * cq;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(e % cq);
+        long long r = e / cq;
+        const int ox = (int)(r % a.Wout); r /= a.Wout;
+        const int oy = (int)(r % a.Hout);
+        const int b = (int)(r / a.Hout);
+        int y0, y1, x0, x1; float ly, lx;
+        src_index(a.sy, oy, a.Hin, y0, y1, ly);
+        src_index(a.sx, ox, a.Win, x0, x1, lx);
+        const float hy = 1.f - ly, hx = 1.f - lx;
+        const long long base = (long long)b * a.Hin * a.Win;
+        if (VEC) {
+            const float4* in4 = reinterpret_cast<const float4*>(a.in);
+            const float4 v00 = in4[(base + (long long)y0 * a.Win + x0) * cq + c];
+            const float4 v01 = in4[(base + (long long)y0 * a.Win + x1) * cq + c];
+            const float4 v10 = in4[(base + (long long)y1 * a.Win + x0) * cq + c];
+            const float4 v11 = in4[(base + (long long)y1 * a.Win + x1) * cq + c];
+            float4 o;
+            o.x = hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x);
+            o.y = hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
+            o.z = hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
+            o.w = hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
+            reinterpret_cast<float4*>(a.out)[e] = o;
+        } else {
+            const float v00 = a.in[(base + (long long)y0 * a.Win + x0) * cq + c];
+            const float v01 = a.in[(base + (long long)y0 * a.Win + x1) * cq + c];
+            const float v10 = a.in[(base + (long long)y1 * a.Win + x0) * cq + c];
+            const float v11 = a.in[(base + (long long)y1 * a.Win + x1) * cq + c];
+            a.out[e] = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+        }
+    }
+}
+
+// candidate destination range [lo, hi] whose stencil can touch source index i (checked exactly inside the loop)
+__device__ __forceinline__ void dst_range(float scale, int i, int nout, int& lo, int& hi) {
+    if (scale <= 0.f) { lo = 0; hi = nout - 1; return; }
+    lo = max(0, (int)floorf((float)(i - 1) / scale) - 1);
+    hi = min(nout - 1, (int)ceilf((float)(i + 1) / scale) + 1);
+}
+__device__ __forceinline__ float axis_weight(float scale, int dst, int nin, int i) {
+    int i0, i1; float l;
+    src_index(scale, dst, nin, i0, i1, l);
+    return (i0 == i ? 1.f - l : 0.f) + (i1 == i ? l : 0.f);
+}
+
+// d_in[b, iy, ix, :] = sum over (oy, ox) of wy(oy, iy) * wx(ox, ix) * d_out[b, oy, ox, :]      (a.in = d_out, a.out = d_in;
+// Hin/Win are the FORWARD input sizes, i.e. the sizes of d_in)
+template <bool VEC>
+__global__ void __launch_bounds__(256) interp_bwd_kernel(InterpArgs a) {
+    pdl_enter();
+    const int cq = VEC ? a.C / 4 : a.C;
+    const long long total = (long long)a.B * a.Hin * a.Win * cq;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(e % cq);
+        long long r = e / cq;
+        const int ix = (int)(r % a.Win); r /= a.Win;
+        const int iy = (int)(r % a.Hin);
+        const int b = (int)(r / a.Hin);
+        int ylo, yhi, xlo, xhi;
+        dst_range(a.sy, iy, a.Hout, ylo, yhi);
+        dst_range(a.sx, ix, a.Wout, xlo, xhi);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const long long base = (long long)b * a.Hout * a.Wout;
+        for (int oy = ylo; oy <= yhi; ++oy) {
+            const float wy = axis_weight(a.sy, oy, a.Hin, iy);
+            if (wy == 0.f) continue;
+            for (int ox = xlo; ox <= xhi; ++ox) {
+                const float w = wy * axis_weight(a.sx, ox, a.Win, ix);
+                if (w == 0.f) continue;
+                const long long o = (base + (long long)oy * a.Wout + ox) * cq + c;
+                if (VEC) {
+                    const float4 g = reinterpret_cast<const float4*>(a.in)[o];
+                    acc.x = fmaf(w, g.x, acc.x); acc.y = fmaf(w, g.y, acc.y);
+                    acc.z = fmaf(w, g.z, acc.z); acc.w = fmaf(w, g.w, acc.w);
+                } else {
+                    acc.x = fmaf(w, a.in[o], acc.x);
+                }
+            }
+        }
+        if (VEC) reinterpret_cast<float4*>(a.out)[e] = acc;
+        else a.out[e] = acc.x;
+    }
+}
+
+static int launch_interp(bool backward, const float* in, float* out, int B, int Hin, int Win, int Hout, int Wout, int C,
+                         cudaStream_t st) {
+    InterpArgs a;
+    a.in = in; a.out = out; a.B = B; a.Hin = Hin; a.Win = Win; a.Hout = Hout; a.Wout = Wout; a.C = C;
+    a.sy = Hout > 1 ? (float)(Hin - 1) / (float)(Hout - 1) : 0.f;       // same float arithmetic as ATen's
+    a.sx = Wout > 1 ? (float)(Win - 1) / (float)(Wout - 1) : 0.f;       // area_pixel_compute_scale<float>(align_corners)
+    const bool vec = C % 4 == 0 && ((uintptr_t)in % 16) == 0 && ((uintptr_t)out % 16) == 0;
+    const long long total = (long long)B * (backward ? Hin * Win : Hout * Wout) * (vec ? C / 4 : C);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (blocks < 1) blocks = 1;
+    if (backward) {
+        if (vec) launch_pdl(interp_bwd_kernel<true>, (int)blocks, 256, 0, st, a);
+        else launch_pdl(interp_bwd_kernel<false>, (int)blocks, 256, 0, st, a);
+    } else {
+        if (vec) launch_pdl(interp_fwd_kernel<true>, (int)blocks, 256, 0, st, a);
+        else launch_pdl(interp_fwd_kernel<false>, (int)blocks, 256, 0, st, a);
+    }
+    return check_launch(backward ? "gb200_interp_bilinear_bwd" : "gb200_interp_bilinear_fwd");
+}
+
+}  // namespace gb200
+
+using namespace gb200;
+
+extern "C" int gb200_interp_bilinear_fwd(int device, const float* in, int B, int Hin, int Win, int C, float* out, int Hout,
+                                         int Wout, void* stream) {
+    use_device(device);
+    GB_REQUIRE(in && out && B >= 1 && Hin >= 1 && Win >= 1 && Hout >= 1 && Wout >= 1 && C >= 1,
+               "gb200_interp_bilinear_fwd: bad arguments");
+    return launch_interp(false, in, out, B, Hin, Win, Hout, Wout, C, as_stream(stream));
+}
+
+extern "C" int gb200_interp_bilinear_bwd(int device, const float* dout, int B, int Hin, int Win, int C, float* din, int Hout,
+                                         int Wout, void* stream) {
+    use_device(device);
+    GB_REQUIRE(dout && din && B >= 1 && Hin >= 1 && Win >= 1 && Hout >= 1 && Wout >= 1 && C >= 1,
+               "gb200_interp_bilinear_bwd: bad arguments");
+    return launch_interp(true, dout, din, B, Hin, Win, Hout, Wout, C, as_stream(stream));
+}

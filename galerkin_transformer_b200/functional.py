@@ -479,6 +479,38 @@ def linear_cat(x1, x2, weight, bias=None):
 
 
 # ------------------------------------------------------------------------------------------
+# Bilinear resize (align_corners=True) of channel-last grids
+# ------------------------------------------------------------------------------------------
+class _InterpFn(torch.autograd.Function):
+    """(B, H, W, C) -> (B, Hout, Wout, C); F.interpolate(mode='bilinear', align_corners=True) of the interpolation
+    scalers (libs/layers.py:431-512, 624-670) on channel-last memory; deterministic gather backward."""
+
+    @staticmethod
+    def forward(ctx, x, Hout, Wout):
+        require_cuda_f32(x)
+        B, H, W, C = x.shape
+        y = torch.empty((B, Hout, Wout, C), dtype=torch.float32, device=x.device)
+        _launch("interp_bilinear", 8.0 * y.numel(), 4.0 * (x.numel() + y.numel()), _lib.load().gb200_interp_bilinear_fwd,
+                _dev(x), ptr(x), B, H, W, C, ptr(y), Hout, Wout, stream_of(x))
+        ctx.shape = (B, H, W, C, Hout, Wout)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, H, W, C, Hout, Wout = ctx.shape
+        dy = dy.contiguous()
+        dx = torch.empty((B, H, W, C), dtype=torch.float32, device=dy.device)
+        _launch("interp_bilinear", 8.0 * dy.numel(), 4.0 * (dx.numel() + dy.numel()),
+                _lib.load().gb200_interp_bilinear_bwd, _dev(dy), ptr(dy), B, H, W, C, ptr(dx), Hout, Wout, stream_of(dy))
+        return dx, None, None
+
+
+def interp_bilinear(x, Hout, Wout):
+    """x: (B, H, W, C) contiguous fp32 CUDA"""
+    return _InterpFn.apply(x.contiguous(), int(Hout), int(Wout))
+
+
+# ------------------------------------------------------------------------------------------
 # Row LayerNorm
 # ------------------------------------------------------------------------------------------
 class _LayerNormFn(torch.autograd.Function):

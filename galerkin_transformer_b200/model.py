@@ -6,11 +6,13 @@ signatures and state_dict layout (scaomath/galerkin-transformer `libs/model.py`)
   SimpleTransformer              model.py:752-942     FourierTransformer2D model.py:945-1184
   FourierTransformer2DLite       model.py:1186-1283
 
-The encoder layers, regressors and every nn.Linear on the path run on the CUDA library; the
-interpolation-CNN down/up-scalers stay stock PyTorch/cuDNN (out of the hot-path scope,
-SURVEY.md section 8f row 1) but are kept in channels-last so no permute copies surround them.
+The encoder layers, regressors and every nn.Linear on the path run on the CUDA library.  Of the
+interpolation-CNN down/up-scalers (the first "next" row) the bilinear resizes run on the
+library's streaming kernel (csrc/interp.cu); their 3x3 convolutions stay stock cuDNN, kept in channels-last so no
+permute copies surround them.
 """
 import copy
+import math
 from collections import defaultdict
 
 import torch
@@ -210,10 +212,15 @@ class Conv2dResBlock(nn.Module):
 
 
 def _resize(x, spec):
-    if isinstance(spec, float):
-        return F.interpolate(x, scale_factor=spec, mode='bilinear', recompute_scale_factor=True,
-                             align_corners=True)
-    return F.interpolate(x, size=tuple(spec), mode='bilinear', align_corners=True)
+    """F.interpolate(x, size=... | scale_factor=..., mode='bilinear', align_corners=True[, recompute_scale_factor=True])
+    for an NCHW view of channel-last memory, on the library's streaming resize kernel (csrc/interp.cu)."""
+    H, W = x.shape[-2:]
+    if isinstance(spec, float):       # recompute_scale_factor=True: only the floor()ed output size reaches the kernel
+        size = (int(math.floor(float(H) * spec)), int(math.floor(float(W) * spec)))
+    else:
+        size = tuple(int(s) for s in spec)
+    y = GF.interp_bilinear(x.permute(0, 2, 3, 1), size[0], size[1])      # a view when x is channels-last
+    return y.permute(0, 3, 1, 2)
 
 
 class Interp2dEncoder(nn.Module):
@@ -267,10 +274,12 @@ class Interp2dUpsample(nn.Module):
         self.interp_mode = interp_mode
 
     def forward(self, x):
-        x = F.interpolate(x, size=self.interp_size[0], mode=self.interp_mode, align_corners=True)
+        if self.interp_mode != 'bilinear':
+            raise NotImplementedError(f"Interp2dUpsample(interp_mode={self.interp_mode!r})")
+        x = _resize(x, self.interp_size[0])
         if self.conv_block:
             x = self.conv(x)
-        return F.interpolate(x, size=self.interp_size[1], mode=self.interp_mode, align_corners=True)
+        return _resize(x, self.interp_size[1])
 
 
 class DownScaler(nn.Module):

@@ -234,6 +234,16 @@ int gb200_spectral_yidft_epilogue(int device, const float* Z, long long R, int n
                                   const float* Wm, const float* bias, int act, float* y, float* zout,
                                   int tensor_cores, void* stream);
 
+/* ------------------------------------------------------------------ grid resize ---------------
+ * Bilinear resize with align_corners = True of a channel-last grid (B, Hin, Win, C) -> (B, Hout, Wout, C): the
+ * F.interpolate(mode='bilinear', align_corners=True) steps of the interpolation scalers
+ * (libs/layers.py:431-512 Interp2dEncoder, :624-670 Interp2dUpsample), which the reference runs on (B, C, H, W).
+ * _bwd: din (B, Hin, Win, C) = adjoint applied to dout (B, Hout, Wout, C); gather formulation, deterministic. */
+int gb200_interp_bilinear_fwd(int device, const float* in, int B, int Hin, int Win, int C, float* out, int Hout, int Wout,
+                              void* stream);
+int gb200_interp_bilinear_bwd(int device, const float* dout, int B, int Hin, int Win, int C, float* din, int Hout,
+                              int Wout, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -316,6 +316,30 @@ def test_attention_core_kernels(B, H, n, dk, p, tc):
     assert dq[:, :dm].abs().max() == 0 and dq[:, 2 * dm:].abs().max() == 0
 
 
+@pytest.mark.parametrize("B,Hin,Win,Hout,Wout,C", [(2, 141, 141, 77, 77, 128), (2, 77, 77, 43, 43, 128),
+                                                    (2, 43, 43, 77, 77, 128), (1, 77, 77, 141, 141, 128),
+                                                    (3, 29, 31, 10, 7, 6), (2, 10, 7, 29, 31, 5), (2, 9, 9, 1, 1, 4),
+                                                    (2, 1, 1, 5, 6, 8), (2, 16, 16, 16, 16, 12)])
+def test_interp_bilinear_matches_torch(B, Hin, Win, Hout, Wout, C):
+    """F.interpolate(mode='bilinear', align_corners=True) forward and its autograd backward (libs/layers.py:493, 506,
+    660, 668), channel-last streaming kernels; the C3 scaler sizes plus ragged / degenerate ones."""
+    x = rn(B, Hin, Win, C).requires_grad_(True)
+    y = GF.interp_bilinear(x, Hout, Wout)
+    cot = rn(B, Hout, Wout, C, seed=1)
+    (gx,) = torch.autograd.grad((y * cot).sum(), [x])
+    xd = x.detach().double().requires_grad_(True)
+    yr = torch.nn.functional.interpolate(xd.permute(0, 3, 1, 2), size=(Hout, Wout), mode="bilinear", align_corners=True)
+    (gr,) = torch.autograd.grad((yr * cot.double().permute(0, 3, 1, 2)).sum(), [xd])
+    # fp32 source-index arithmetic (scale * dst with indices up to 140) puts ~1e-5 of slack on the interpolation weight,
+    # exactly as in ATen's own fp32 kernel; against exact fp64 weights that is a few 1e-6 in relative L2
+    assert rel_l2(y, yr.permute(0, 2, 3, 1)) < 2e-5, rel_l2(y, yr.permute(0, 2, 3, 1))
+    assert rel_l2(gx, gr) < 2e-5, rel_l2(gx, gr)
+    # and the fp32 ATen kernel itself (same float source-index arithmetic): agreement to the last bits
+    y32 = torch.nn.functional.interpolate(x.detach().permute(0, 3, 1, 2), size=(Hout, Wout), mode="bilinear",
+                                          align_corners=True).permute(0, 2, 3, 1)
+    assert (y - y32).abs().max() <= 2e-6 * max(1.0, float(y32.abs().max())), float((y - y32).abs().max())
+
+
 @pytest.mark.parametrize("T,H,dk", [(777, 4, 32), (500, 4, 12), (1000, 1, 96), (333, 2, 16)])
 def test_headnorm_fwd_bwd(T, H, dk):
     """(4,32) and (2,16) take the coalesced float4/shuffle kernels, the others the generic ones."""
