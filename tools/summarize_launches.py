@@ -13,7 +13,10 @@ for r in rows[1:]:
         continue
     v = float(r[iv].replace(",", ""))
     v = v / 1e3 if r[iu] in ("ns", "nsecond") else (v * 1e3 if r[iu] in ("ms", "msecond") else v)     # -> us
-    name = re.sub(r"<.*", "", r[ik])
+    if "spin_kernel" in r[ik]:          # torch.cuda._sleep of bench.py's attribution pass, not part of a step
+        continue
+    name = re.sub(r"<unnamed>::", "", r[ik])
+    name = re.sub(r"<.*", "", name)
     name = re.sub(r"\(.*", "", name).strip()
     if name.startswith("void "):
         name = name[5:]
