@@ -237,6 +237,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--attn-dropout", default="reference", choices=["reference", "off"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-parts", action="store_true", help="skip the encoder-only / decoder-only timings")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -436,6 +437,48 @@ def main():
                                "attribution pass after the timed region, launches pre-queued behind a spin kernel "
                                "so events bracket execution, not host launch latency",
                         native_ms_per_step=round(native_ms, 3))
+    # ---- the encoder stack and the decoder timed on their own (same protocol: graph replay, L2 flush) ----
+    parts = None
+    if rank == 0 and graphed is not None and not args.no_parts:
+        log("parts: encoder stack / decoder alone")
+
+        def time_part(fn, inputs, params):
+            g = GraphedStep(fn, inputs, params, warmup=3)
+            for _ in range(3):
+                g.replay()
+            ss = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+            ee = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+            for i in range(args.steps):
+                flush.fill_(float(i))
+                ss[i].record()
+                g.replay()
+                ee[i].record()
+            torch.cuda.synchronize()
+            return sum(s.elapsed_time(e) for s, e in zip(ss, ee)) / args.steps
+
+        def enc_fn(x_, p_):
+            for layer in model.encoder_layers:
+                x_ = layer(x_, p_)
+            return x_.square().mean()
+
+        def dec_fn(x_, g_):
+            y_ = model.regressor(x_, grid=g_)
+            return (y_[0] if isinstance(y_, tuple) else y_).square().mean()
+
+        gen = torch.Generator(device=dev).manual_seed(7)
+        xe = torch.randn(BATCH, pos.shape[1], 128, device=dev, generator=gen)
+        xd = torch.randn(BATCH, grid.shape[1], grid.shape[2], 128, device=dev, generator=gen)
+        enc_ms = time_part(enc_fn, [xe, pos], list(model.encoder_layers.parameters()))
+        dec_ms = time_part(dec_fn, [xd, grid], list(model.regressor.parameters()))
+        T = BATCH * pos.shape[1]
+        parts = dict(encoder_stack=dict(ms_per_step=round(enc_ms, 4), input=f"x ({BATCH},{pos.shape[1]},128), 10 layers, "
+                                        "fwd+bwd w.r.t. parameters (encoder_memory_profile.py protocol)",
+                                        tokens_per_s=round(T / (enc_ms * 1e-3)),
+                                        alg_gflop=125.0, alg_tflops=round(125.0 / enc_ms, 2)),
+                     decoder=dict(ms_per_step=round(dec_ms, 4), input=f"x ({BATCH},{grid.shape[1]},{grid.shape[2]},128): "
+                                  "fc(cat[x,grid]) -> 2x SpectralConv2d(32, 12 modes) -> 32-128-1 head, fwd+bwd w.r.t. "
+                                  "parameters", grid_points_per_s=round(BATCH * POINTS_PER_SAMPLE / (dec_ms * 1e-3))),
+                     note="full model = downscaler + encoder stack + upscaler + decoder (+ loss); SURVEY.md 8(d)")
     if world > 1:
         dist.barrier()
 
@@ -446,6 +489,8 @@ def main():
                    e2e=dict(value=e2e_value, unit="grid-points/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4),
                    gpu_launches=int(gpu_launches), wall_s_timed_region=round(wall, 3),
                    grad_bucket_bytes=bucket.nbytes, roofline=roofline, kernels=kernels[:12])
+        if parts is not None:
+            out["parts"] = parts
         if world == 1 and not args.no_cpu_baseline:
             log("cpu baseline (oracle on host cores)")
             cval, csec, threads = cpu_reference_run(3, 1, BATCH)

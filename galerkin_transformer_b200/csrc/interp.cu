@@ -63,10 +63,11 @@ __global__ void __launch_bounds__(256) interp_fwd_kernel(InterpArgs a) {
     }
 }
 
-// candidate destination range [lo, hi] whose stencil can touch source index i (checked exactly inside the loop)
+// candidate destination range [lo, hi] whose stencil can touch source index i: scale * dst in [i - 1, i + 1), with one
+// index of slack on the open end (membership is decided exactly by axis_weight)
 __device__ __forceinline__ void dst_range(float scale, int i, int nout, int& lo, int& hi) {
     if (scale <= 0.f) { lo = 0; hi = nout - 1; return; }
-    lo = max(0, (int)floorf((float)(i - 1) / scale) - 1);
+    lo = max(0, (int)floorf((float)(i - 1) / scale));
     hi = min(nout - 1, (int)ceilf((float)(i + 1) / scale) + 1);
 }
 __device__ __forceinline__ float axis_weight(float scale, int dst, int nin, int i) {
@@ -76,10 +77,12 @@ __device__ __forceinline__ float axis_weight(float scale, int dst, int nin, int 
 }
 
 // d_in[b, iy, ix, :] = sum over (oy, ox) of wy(oy, iy) * wx(ox, ix) * d_out[b, oy, ox, :]      (a.in = d_out, a.out = d_in;
-// Hin/Win are the FORWARD input sizes, i.e. the sizes of d_in)
+// Hin/Win are the FORWARD input sizes, i.e. the sizes of d_in).  The per-axis weights of the (at most MAXR) candidate
+// rows / columns are computed once per thread; wider ranges (resize ratios above ~3x) take the generic double loop.
 template <bool VEC>
 __global__ void __launch_bounds__(256) interp_bwd_kernel(InterpArgs a) {
     pdl_enter();
+    constexpr int MAXR = 8;
     const int cq = VEC ? a.C / 4 : a.C;
     const long long total = (long long)a.B * a.Hin * a.Win * cq;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
@@ -94,19 +97,46 @@ __global__ void __launch_bounds__(256) interp_bwd_kernel(InterpArgs a) {
         dst_range(a.sx, ix, a.Wout, xlo, xhi);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         const long long base = (long long)b * a.Hout * a.Wout;
-        for (int oy = ylo; oy <= yhi; ++oy) {
-            const float wy = axis_weight(a.sy, oy, a.Hin, iy);
-            if (wy == 0.f) continue;
-            for (int ox = xlo; ox <= xhi; ++ox) {
-                const float w = wy * axis_weight(a.sx, ox, a.Win, ix);
-                if (w == 0.f) continue;
-                const long long o = (base + (long long)oy * a.Wout + ox) * cq + c;
-                if (VEC) {
-                    const float4 g = reinterpret_cast<const float4*>(a.in)[o];
-                    acc.x = fmaf(w, g.x, acc.x); acc.y = fmaf(w, g.y, acc.y);
-                    acc.z = fmaf(w, g.z, acc.z); acc.w = fmaf(w, g.w, acc.w);
-                } else {
-                    acc.x = fmaf(w, a.in[o], acc.x);
+        const int ny = yhi - ylo + 1, nx = xhi - xlo + 1;
+        if (ny <= MAXR && nx <= MAXR) {
+            float wy[MAXR], wx[MAXR];
+#pragma unroll
+            for (int u = 0; u < MAXR; ++u) {
+                wy[u] = u < ny ? axis_weight(a.sy, ylo + u, a.Hin, iy) : 0.f;
+                wx[u] = u < nx ? axis_weight(a.sx, xlo + u, a.Win, ix) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < MAXR; ++u) {
+                if (wy[u] == 0.f) continue;
+#pragma unroll
+                for (int v = 0; v < MAXR; ++v) {
+                    const float w = wy[u] * wx[v];
+                    if (w == 0.f) continue;
+                    const long long o = (base + (long long)(ylo + u) * a.Wout + (xlo + v)) * cq + c;
+                    if (VEC) {
+                        const float4 g = reinterpret_cast<const float4*>(a.in)[o];
+                        acc.x = fmaf(w, g.x, acc.x); acc.y = fmaf(w, g.y, acc.y);
+                        acc.z = fmaf(w, g.z, acc.z); acc.w = fmaf(w, g.w, acc.w);
+                    } else {
+                        acc.x = fmaf(w, a.in[o], acc.x);
+                    }
+                }
+            }
+        } else {
+            for (int oy = ylo; oy <= yhi; ++oy) {
+                const float wyv = axis_weight(a.sy, oy, a.Hin, iy);
+                if (wyv == 0.f) continue;
+                for (int ox = xlo; ox <= xhi; ++ox) {
+                    const float w = wyv * axis_weight(a.sx, ox, a.Win, ix);
+                    if (w == 0.f) continue;
+                    const long long o = (base + (long long)oy * a.Wout + ox) * cq + c;
+                    if (VEC) {
+                        const float4 g = reinterpret_cast<const float4*>(a.in)[o];
+                        acc.x = fmaf(w, g.x, acc.x); acc.y = fmaf(w, g.y, acc.y);
+                        acc.z = fmaf(w, g.z, acc.z); acc.w = fmaf(w, g.w, acc.w);
+                    } else {
+                        acc.x = fmaf(w, a.in[o], acc.x);
+                    }
                 }
             }
         }
