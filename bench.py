@@ -238,6 +238,8 @@ def main():
     ap.add_argument("--attn-dropout", default="reference", choices=["reference", "off"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-parts", action="store_true", help="skip the encoder-only / decoder-only timings")
+    ap.add_argument("--batch-streams", type=int, default=int(os.environ.get("GB200_BATCH_STREAMS", "1")),
+                    help="split the per-GPU batch into this many concurrent micro-batch chains inside the graph")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -250,7 +252,7 @@ def main():
                           + args.attn_dropout,
                   l2="256 MiB buffer written between timed steps (L2 flush)",
                   launch="eager" if args.no_graph else "whole fwd+bwd step replayed from one CUDA graph",
-                  gemm_precision=args.precision,
+                  gemm_precision=args.precision, micro_batch_chains=args.batch_streams,
                   backward_streams="dW / db launches on 2 side streams (parallel graph branches)"
                   if os.environ.get("GB200_BWD_STREAMS", "1") != "0" else "off")
 
@@ -301,7 +303,8 @@ def main():
     graphed, launches_per_step = None, None
     if not args.no_graph:
         c0 = _lib.launch_count()
-        graphed = GraphedStep(loss_fn, [node, pos, grid, target], model.parameters(), warmup=3)
+        graphed = GraphedStep(loss_fn, [node, pos, grid, target], model.parameters(), warmup=3,
+                              batch_streams=args.batch_streams)
         # 3 eager warm-ups + 1 capture pass, all with identical launch sequences
         launches_per_step = (_lib.launch_count() - c0) // 4
         log(f"captured CUDA graph: {launches_per_step} libgalerkin_b200 kernels per step")

@@ -138,7 +138,9 @@ class _Fork:
     def side(self, i):
         if not _BWD_STREAMS:
             return contextlib.nullcontext()
-        pool = _side_streams.setdefault(self.device.index, [])
+        # one pool per launching stream: concurrent micro-batch chains (graphs.py batch_streams) must not share side
+        # streams, or their joins would serialise the chains
+        pool = _side_streams.setdefault((self.device.index, self.main.cuda_stream), [])
         while len(pool) <= i:
             pool.append(torch.cuda.Stream(device=self.device))
         s = pool[i]

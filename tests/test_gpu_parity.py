@@ -291,6 +291,37 @@ def test_graphed_step_matches_eager_and_refreshes_dropout(precision):
     assert a != b
 
 
+@pytest.mark.parametrize("chains", [2, 4])
+def test_micro_batch_chains_give_the_full_batch_gradient(chains, precision):
+    """GraphedStep(batch_streams=k): k concurrent micro-batch chains inside one captured graph produce the loss and
+    the gradients of the full batch (per-sample-independent model, batch-mean loss)."""
+    from galerkin_transformer_b200.graphs import GraphedStep
+    from bench import c3_config, c3_inputs
+    torch.manual_seed(6)
+    cfg = c3_config(dropout_free=True)
+    cfg["num_encoder_layers"] = 2
+    model = G.FourierTransformer2D(**cfg).to(DEV)
+    G.set_attn_dropout(model, "off")
+    data = c3_inputs(4, DEV)
+
+    def loss_fn(n_, p_, g_, t_):
+        return ((model(n_, None, p_, g_)["preds"] - t_) ** 2).mean()
+
+    graphed = GraphedStep(loss_fn, data, model.parameters(), batch_streams=chains)
+    outs = []
+    for _ in range(2):
+        l = graphed(*data)
+        outs.append((l.item(), [g.clone() for g in graphed.static_grads]))
+    for p_ in model.parameters():
+        p_.grad = None
+    full = loss_fn(*data)
+    full.backward()
+    for lv, grads in outs:
+        assert abs(lv - full.item()) < 1e-5 * abs(full.item()) + 1e-9
+        for g, p_ in zip(grads, model.parameters()):
+            assert rel_l2(g, p_.grad) < (1e-4 if G.get_precision() == "fp32" else 2e-2), rel_l2(g, p_.grad)
+
+
 @pytest.mark.parametrize("B,H,n,dk,p", [(2, 4, 200, 48, 2), (1, 2, 333, 16, 1), (2, 1, 130, 62, 2)])
 def test_fourier_quadratic_kernels_match_oracle(B, H, n, dk, p, precision):
     """(Q K^T) V with an explicit n x n keep-mask (the reference's dropout made reproducible): forward, the
