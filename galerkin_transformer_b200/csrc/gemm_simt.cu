@@ -469,25 +469,39 @@ __global__ void __launch_bounds__(256) epilogue_bwd_bias_kernel(const float4* __
     if (drop_p > 0.f && seed_off) seed += *seed_off;
     const int rowq = N / 4, q = threadIdx.x % rowq, rsub = threadIdx.x / rowq, rpb = 256 / rowq;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = blockIdx.x * rpb + rsub; r < M; r += gridDim.x * rpb) {
-        const long long e = (long long)r * rowq + q;
-        float4 v = dy[e];
-        v.x *= rscale; v.y *= rscale; v.z *= rscale; v.w *= rscale;
-        if (drop_p > 0.f) {
-            const float4 ds = dropout_scale4(drop_p, seed, (unsigned long long)e * 4);
-            v.x *= ds.x; v.y *= ds.y; v.z *= ds.z; v.w *= ds.w;
+    constexpr int RU = 4;                       // rows in flight per thread: all loads issued before the Philox math
+    const int stride = gridDim.x * rpb;
+    for (int r0 = blockIdx.x * rpb + rsub; r0 < M; r0 += RU * stride) {
+        float4 v[RU], rr[RU];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            const int r = r0 + u * stride;
+            if (r < M) {
+                v[u] = dy[(long long)r * rowq + q];
+                if (ACT != ACT_NONE) rr[u] = ref[(long long)r * rowq + q];
+            }
         }
-        if (ACT == ACT_RELU) {
-            const float4 rr = ref[e];
-            v.x = rr.x > 0.f ? v.x : 0.f; v.y = rr.y > 0.f ? v.y : 0.f;
-            v.z = rr.z > 0.f ? v.z : 0.f; v.w = rr.w > 0.f ? v.w : 0.f;
-        } else if (ACT == ACT_SILU) {
-            const float4 rr = ref[e];
-            v.x *= act_grad(ACT_SILU, rr.x); v.y *= act_grad(ACT_SILU, rr.y);
-            v.z *= act_grad(ACT_SILU, rr.z); v.w *= act_grad(ACT_SILU, rr.w);
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            const int r = r0 + u * stride;
+            if (r >= M) break;
+            const long long e = (long long)r * rowq + q;
+            float4 w = v[u];
+            w.x *= rscale; w.y *= rscale; w.z *= rscale; w.w *= rscale;
+            if (drop_p > 0.f) {
+                const float4 ds = dropout_scale4(drop_p, seed, (unsigned long long)e * 4);
+                w.x *= ds.x; w.y *= ds.y; w.z *= ds.z; w.w *= ds.w;
+            }
+            if (ACT == ACT_RELU) {
+                w.x = rr[u].x > 0.f ? w.x : 0.f; w.y = rr[u].y > 0.f ? w.y : 0.f;
+                w.z = rr[u].z > 0.f ? w.z : 0.f; w.w = rr[u].w > 0.f ? w.w : 0.f;
+            } else if (ACT == ACT_SILU) {
+                w.x *= act_grad(ACT_SILU, rr[u].x); w.y *= act_grad(ACT_SILU, rr[u].y);
+                w.z *= act_grad(ACT_SILU, rr[u].z); w.w *= act_grad(ACT_SILU, rr[u].w);
+            }
+            gout[e] = w;
+            acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
         }
-        gout[e] = v;
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
     red[threadIdx.x] = acc;
     __syncthreads();

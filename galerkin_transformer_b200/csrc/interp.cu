@@ -27,17 +27,17 @@ __device__ __forceinline__ void src_index(float scale, int dst, int nin, int& i0
 template <bool VEC>
 __global__ void __launch_bounds__(256) interp_fwd_kernel(InterpArgs a) {
     pdl_enter();
+    // one output row (b, oy) per CTA pass; threads stride over (ox, channel quad): 32-bit index arithmetic only
     const int cq = VEC ? a.C / 4 : a.C;
-    const long long total = (long long)a.B * a.Hout * a.Wout * cq;
-    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
-         e += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(e % cq);
-        long long r = e / cq;
-        const int ox = (int)(r % a.Wout); r /= a.Wout;
-        const int oy = (int)(r % a.Hout);
-        const int b = (int)(r / a.Hout);
-        int y0, y1, x0, x1; float ly, lx;
-        src_index(a.sy, oy, a.Hin, y0, y1, ly);
+    const int rowlen = a.Wout * cq;
+    for (int row = blockIdx.x; row < a.B * a.Hout; row += gridDim.x) {
+      const int b = row / a.Hout, oy = row % a.Hout;
+      int y0, y1; float ly;
+      src_index(a.sy, oy, a.Hin, y0, y1, ly);
+      for (int t = threadIdx.x; t < rowlen; t += blockDim.x) {
+        const int ox = t / cq, c = t % cq;
+        const long long e = (long long)row * rowlen + t;
+        int x0, x1; float lx;
         src_index(a.sx, ox, a.Win, x0, x1, lx);
         const float hy = 1.f - ly, hx = 1.f - lx;
         const long long base = (long long)b * a.Hin * a.Win;
@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(256) interp_fwd_kernel(InterpArgs a) {
             const float v11 = a.in[(base + (long long)y1 * a.Win + x1) * cq + c];
             a.out[e] = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
         }
+      }
     }
 }
 
@@ -84,16 +85,15 @@ __global__ void __launch_bounds__(256) interp_bwd_kernel(InterpArgs a) {
     pdl_enter();
     constexpr int MAXR = 8;
     const int cq = VEC ? a.C / 4 : a.C;
-    const long long total = (long long)a.B * a.Hin * a.Win * cq;
-    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
-         e += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(e % cq);
-        long long r = e / cq;
-        const int ix = (int)(r % a.Win); r /= a.Win;
-        const int iy = (int)(r % a.Hin);
-        const int b = (int)(r / a.Hin);
-        int ylo, yhi, xlo, xhi;
-        dst_range(a.sy, iy, a.Hout, ylo, yhi);
+    const int rowlen = a.Win * cq;
+    for (int row = blockIdx.x; row < a.B * a.Hin; row += gridDim.x) {
+      const int b = row / a.Hin, iy = row % a.Hin;
+      int ylo, yhi;
+      dst_range(a.sy, iy, a.Hout, ylo, yhi);
+      for (int t = threadIdx.x; t < rowlen; t += blockDim.x) {
+        const int ix = t / cq, c = t % cq;
+        const long long e = (long long)row * rowlen + t;
+        int xlo, xhi;
         dst_range(a.sx, ix, a.Wout, xlo, xhi);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         const long long base = (long long)b * a.Hout * a.Wout;
@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(256) interp_bwd_kernel(InterpArgs a) {
         }
         if (VEC) reinterpret_cast<float4*>(a.out)[e] = acc;
         else a.out[e] = acc.x;
+      }
     }
 }
 
@@ -152,8 +153,7 @@ static int launch_interp(bool backward, const float* in, float* out, int B, int 
     a.sy = Hout > 1 ? (float)(Hin - 1) / (float)(Hout - 1) : 0.f;       // same float arithmetic as ATen's
     a.sx = Wout > 1 ? (float)(Win - 1) / (float)(Wout - 1) : 0.f;       // area_pixel_compute_scale<float>(align_corners)
     const bool vec = C % 4 == 0 && ((uintptr_t)in % 16) == 0 && ((uintptr_t)out % 16) == 0;
-    const long long total = (long long)B * (backward ? Hin * Win : Hout * Wout) * (vec ? C / 4 : C);
-    long long blocks = (total + 255) / 256;
+    long long blocks = (long long)B * (backward ? Hin : Hout);      // one grid row per CTA pass
     if (blocks > 148 * 32) blocks = 148 * 32;
     if (blocks < 1) blocks = 1;
     if (backward) {
