@@ -16,6 +16,7 @@ Lines printed (rank 0): one JSON object, see the keys in `main`.
   e2e    : same metric through the public module API with pinned HOST inputs; H2D copies of the
            step's inputs and the D2H read of the loss are inside the timed region
   roofline / kernels : per-launch CUDA-event attribution pass run right after the timed region
+  parts  : the 10-layer encoder stack and the spectral decoder timed alone, same protocol
   cpu_baseline : the oracle (CPU restatement of the reference) timed on this box's host cores
 --impl reference : the oracle on CPU only, same metric/config (the reference is pure PyTorch and
   cannot travel to the GPU box; the oracle is pinned to it by tests/golden).
