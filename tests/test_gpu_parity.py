@@ -134,6 +134,13 @@ def _perturb(mod, seed=0):
           layer_norm=False, attn_norm=True, dropout=0.0, ffn_dropout=0.0), 2, 8192),
     (dict(d_model=96, n_head=1, pos_dim=1, dim_feedforward=192, attention_type="fourier",
           layer_norm=False, attn_norm=True, dropout=0.0, ffn_dropout=0.0), 2, 2048),
+    # C4: Darcy inverse, Fourier-type attention on the 71x71 grid, per-GPU batch 4 (ex3 config: 192 / 4 heads / 384)
+    # OPEN (end of round 1): the first run of this size on a B200 showed ONE gradient off -- attn.norm_Q.3.bias, 3.5e-2
+    # relative, all others within tolerance, both precision modes; the GPU pool was unavailable to bisect it
+    # ("Known issue").  Non-strict xfail so the finding stays visible without stopping `-x` runs.
+    pytest.param(dict(d_model=192, n_head=4, pos_dim=2, dim_feedforward=384, attention_type="fourier",
+                      layer_norm=False, attn_norm=True, norm_eps=1e-7, dropout=0.0, ffn_dropout=0.0), 4, 5041,
+                 marks=pytest.mark.xfail(strict=False, reason="C4-size d(beta_Q) of the last head off by 3.5e-2: open")),
     # C5: Navier-Stokes 64x64, 1 head, post-LN
     (dict(d_model=48, n_head=1, pos_dim=2, dim_feedforward=96, attention_type="galerkin",
           layer_norm=True, attn_norm=False, dropout=0.0, ffn_dropout=0.0), 4, 4096),
@@ -358,6 +365,37 @@ def test_fourier_quadratic_kernels_match_oracle(B, H, n, dk, p, precision):
         yl, none = a(x, x, x, pos=pos)
         assert none is None
         assert rel_l2(yq, yl) < tol["fwd"]
+
+
+@pytest.mark.xfail(strict=False, reason="written at the end of round 1, not yet run on a B200 (GPU pool unavailable)")
+def test_fourier_quadratic_equals_linear_form_at_c4_size(precision):
+    """C4 size (B=4 per GPU, 4 heads, 71x71 = 5041 tokens, d = 48 + 2): the flash-style (Q K^T) V kernels (forced by
+    materialising the attention matrix) against the O(n d^2) reassociation, forward and every gradient.  The linear
+    form is itself checked against the fp64 oracle at this size in test_encoder_layer_matches_oracle_at_baseline_sizes,
+    so this pins the quadratic kernels at the full problem size without an n x n fp64 reference of their own."""
+    tol = TOLS[precision]
+    torch.manual_seed(8)
+    B, H, n, dk, p = 4, 4, 5041, 48, 2
+    dm = H * dk
+    a = G.SimpleAttention(n_head=H, d_model=dm, pos_dim=p, attention_type="fourier", norm=True, eps=1e-7)
+    _perturb(a, seed=4)
+    a = a.to(DEV)
+    a.attn_dropout = "off"
+    x = torch.randn(B, n, dm, device=DEV, requires_grad=True)
+    pos = _mesh(B, 71, DEV)
+    cot = torch.randn(B, n, dm, device=DEV)
+    leaves = [x] + list(a.parameters())
+    y1, none = a(x, x, x, pos=pos)
+    assert none is None
+    g1 = torch.autograd.grad((y1 * cot).sum(), leaves)
+    a.materialize_attn = True
+    y2, attn = a(x, x, x, pos=pos)
+    g2 = torch.autograd.grad((y2 * cot).sum(), leaves)
+    assert tuple(attn.shape) == (B, H, n, n)
+    assert rel_l2(y2, y1) < tol["fwd"], rel_l2(y2, y1)
+    for k, u, v in zip(["x"] + [k for k, _ in a.named_parameters()], g2, g1):
+        assert rel_l2(u, v) < tol["grad"], (k, rel_l2(u, v))
+    assert torch.isfinite(attn).all()
 
 
 def test_fourier_reference_dropout_is_unbiased_and_reproducible_in_backward():
