@@ -105,6 +105,16 @@ class SimpleAttention(nn.Module):
             x = GF.linear(x, self.fc.weight, self.fc.bias)
         return x, attn_weight
 
+    def _packed_parts(self):
+        """Parameters in the order of the packed vector [W_qkv | b_qkv | gamma_1 | beta_1 | gamma_2 | beta_2] that
+        functional._unpack_attention_params slices: block 1 = norm_K, block 2 = norm_V (Galerkin) or norm_Q (Fourier)."""
+        parts = [lin.weight for lin in self.linears] + [lin.bias for lin in self.linears]
+        if self.add_norm:
+            second = self.norm_V if self.attention_type in _GALERKIN else self.norm_Q
+            for mods, attr in ((self.norm_K, "weight"), (self.norm_K, "bias"), (second, "weight"), (second, "bias")):
+                parts += [getattr(m, attr) for m in mods]
+        return parts
+
     def forward_heads(self, query, key, value, pos=None, mask=None, weight=None):
         """Everything up to (excluding) the output `fc`: returns the head-merged
         (B, n, H*(d_k+pos_dim)) tensor so a caller can fuse fc with its residual add."""
@@ -122,13 +132,7 @@ class SimpleAttention(nn.Module):
         d = self.d_k + p
         self_attn = (query is key) and (key is value)
         # W_qkv (3 d_model, d_model), b_qkv and the per-head LayerNorm tables, assembled by one pack launch
-        dm = self.n_head * self.d_k
-        parts = [lin.weight for lin in self.linears] + [lin.bias for lin in self.linears]
-        if self.add_norm:
-            second = self.norm_V if self.attention_type in _GALERKIN else self.norm_Q
-            for mods, attr in ((self.norm_K, "weight"), (self.norm_K, "bias"), (second, "weight"), (second, "bias")):
-                parts += [getattr(m, attr) for m in mods]
-        flat = GF.pack(parts)     # [W_qkv | b_qkv | gamma_1 | beta_1 | gamma_2 | beta_2]; its gradient comes back flat too
+        flat = GF.pack(self._packed_parts())     # its gradient comes back as one flat buffer too
 
         keep = self._next_mask
         self._next_mask = None

@@ -116,3 +116,92 @@ def test_scaler_sizes():
     down, up = G.scaler_sizes(211, 71)
     assert up[1] == (211, 211)
     assert G.scaler_sizes(141, 43, scale_factor=False)[0] == ((77, 77), (43, 43))
+
+
+@pytest.mark.parametrize("attention_type,norm", [("galerkin", True), ("fourier", True), ("galerkin", False)])
+def test_packed_attention_parameter_layout(attention_type, norm):
+    """The one-launch parameter pack (gb200_pack) and the slices the kernels / the flat gradient use must agree:
+    concat(_packed_parts()) unpacks to W_qkv = [W_q; W_k; W_v], b_qkv and the (H, d_k) LayerNorm tables."""
+    from galerkin_transformer_b200.functional import _unpack_attention_params
+    H, dk = 3, 8
+    dm = H * dk
+    a = G.SimpleAttention(n_head=H, d_model=dm, pos_dim=2, attention_type=attention_type, norm=norm)
+    with torch.no_grad():
+        for p in a.parameters():
+            p.copy_(torch.randn_like(p))
+    flat = torch.cat([p.detach().reshape(-1) for p in a._packed_parts()])
+    w, b, g1, b1, g2, b2 = _unpack_attention_params(flat, dm, H, dk, norm)
+    assert torch.equal(w, torch.cat([l.weight for l in a.linears], 0))
+    assert torch.equal(b, torch.cat([l.bias for l in a.linears], 0))
+    if not norm:
+        assert g1 is None and b2 is None and flat.numel() == 3 * dm * dm + 3 * dm
+        return
+    second = a.norm_V if attention_type == "galerkin" else a.norm_Q
+    assert torch.equal(g1, torch.stack([m.weight for m in a.norm_K])) and torch.equal(b1, torch.stack([m.bias for m in a.norm_K]))
+    assert torch.equal(g2, torch.stack([m.weight for m in second])) and torch.equal(b2, torch.stack([m.bias for m in second]))
+    assert flat.numel() == 3 * dm * dm + 3 * dm + 4 * dm
+
+
+def _resize_restated(x, Hout, Wout, backward_of=None):
+    """csrc/interp.cu restated in numpy float32: forward taps / weights, and the GATHER backward with its candidate
+    ranges (dst_range) -- the algorithm, not the kernel."""
+    import math
+    import numpy as np
+    f32 = np.float32
+    B_, Hin, Win, C = x.shape if backward_of is None else backward_of
+
+    def axis(nin, nout):
+        scale = f32(nin - 1) / f32(nout - 1) if nout > 1 else f32(0)
+        s = (scale * np.arange(nout, dtype=f32)).astype(f32)
+        i0 = np.minimum(s.astype(np.int64), nin - 1)
+        i1 = i0 + (i0 < nin - 1)
+        l = (s - i0.astype(f32)).astype(f32)
+        return scale, i0, i1, l
+    sy, y0, y1, ly = axis(Hin, Hout)
+    sx, x0, x1, lx = axis(Win, Wout)
+    if backward_of is None:
+        v = x.astype(f32)
+        top = v[:, y0][:, :, x0] * (1 - lx)[None, None, :, None] + v[:, y0][:, :, x1] * lx[None, None, :, None]
+        bot = v[:, y1][:, :, x0] * (1 - lx)[None, None, :, None] + v[:, y1][:, :, x1] * lx[None, None, :, None]
+        return top * (1 - ly)[None, :, None, None] + bot * ly[None, :, None, None]
+
+    def ranges_and_weights(scale, nin, nout, i0, i1, l):
+        out = []
+        for i in range(nin):
+            if scale <= 0:
+                lo, hi = 0, nout - 1
+            else:
+                lo = max(0, int(math.floor(float(f32(i - 1) / scale))))
+                hi = min(nout - 1, int(math.ceil(float(f32(i + 1) / scale))) + 1)
+            w = [(d, (1 - l[d] if i0[d] == i else 0.0) + (l[d] if i1[d] == i else 0.0)) for d in range(lo, hi + 1)]
+            touched = {d for d in range(nout) if i0[d] == i or i1[d] == i}
+            assert touched <= set(range(lo, hi + 1)), "candidate range misses a contributing output index"
+            out.append([(d, wd) for d, wd in w if wd != 0.0])
+        return out
+    wy = ranges_and_weights(sy, Hin, Hout, y0, y1, ly)
+    wx = ranges_and_weights(sx, Win, Wout, x0, x1, lx)
+    g = x.astype(f32)                                   # d_out (B, Hout, Wout, C)
+    din = np.zeros((B_, Hin, Win, C), dtype=f32)
+    for iy in range(Hin):
+        for ix in range(Win):
+            for oy, a_ in wy[iy]:
+                for ox, b_ in wx[ix]:
+                    din[:, iy, ix] += f32(a_ * b_) * g[:, oy, ox]
+    return din
+
+
+@pytest.mark.parametrize("Hin,Win,Hout,Wout", [(15, 15, 9, 9), (9, 9, 15, 15), (10, 7, 29, 31), (13, 11, 5, 4), (6, 6, 1, 1),
+                                               (1, 1, 4, 5), (8, 8, 8, 8)])
+def test_resize_algorithm_restated_on_cpu(Hin, Win, Hout, Wout):
+    """The algorithm of csrc/interp.cu (taps, fp32 source indices, gather backward over dst_range candidates) equals
+    F.interpolate(mode='bilinear', align_corners=True) and its autograd adjoint (libs/layers.py:493, 506, 660, 668)."""
+    import numpy as np
+    torch.manual_seed(0)
+    x = torch.randn(2, Hin, Win, 3, dtype=torch.float64, requires_grad=True)
+    y = torch.nn.functional.interpolate(x.permute(0, 3, 1, 2), size=(Hout, Wout), mode="bilinear", align_corners=True)
+    cot = torch.randn(2, Hout, Wout, 3, dtype=torch.float64)
+    (gx,) = torch.autograd.grad((y * cot.permute(0, 3, 1, 2)).sum(), [x])
+    yr = _resize_restated(x.detach().numpy(), Hout, Wout)
+    gr = _resize_restated(cot.numpy(), Hout, Wout, backward_of=(2, Hin, Win, 3))
+    assert np.abs(yr - y.detach().permute(0, 2, 3, 1).numpy()).max() < 1e-5
+    assert np.abs(gr - gx.numpy()).max() < 1e-5
