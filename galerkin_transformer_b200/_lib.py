@@ -28,6 +28,17 @@ class HeadOperand(ctypes.Structure):
 
 _HOP = ctypes.POINTER(HeadOperand)
 
+
+class EncoderParams(ctypes.Structure):
+    """mirror of gb200_encoder_params (include/galerkin_b200.h)"""
+    _fields_ = [(k, c_vp) for k in ("wq", "wk", "wv", "bq", "bk", "bv")] + \
+               [("gamma_k", c_vp * 8), ("beta_k", c_vp * 8), ("gamma_v", c_vp * 8), ("beta_v", c_vp * 8)] + \
+               [(k, c_vp) for k in ("wfc", "bfc", "w1", "b1", "w2", "b2")] + \
+               [(k, c_int) for k in ("d_model", "n_head", "pos_dim", "d_ff")]
+
+
+_ENCP = ctypes.POINTER(EncoderParams)
+
 # name -> (restype, argtypes); must list every symbol of include/galerkin_b200.h
 SIGNATURES = {
     "gb200_version": (c_int, []),
@@ -92,6 +103,13 @@ SIGNATURES = {
                                        c_vp, c_vp, c_vp, c_int, c_vp]),
     "gb200_spectral_yidft_epilogue": (c_int, [c_int, c_vp, c_ll, c_int, c_int, c_int, c_vp, c_float, c_int,
                                               c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp]),
+    "gb200_encoder_supported": (c_int, [c_int] * 4),
+    "gb200_encoder_pack_bytes": (c_sz, [c_int] * 4),
+    "gb200_encoder_pack": (c_int, [c_int, _ENCP, c_vp, c_vp]),
+    "gb200_encoder_workspace_bytes": (c_sz, [c_int] * 5),
+    "gb200_encoder_layer_fwd": (c_int, [c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_int, c_int, c_float,
+                                        c_float, c_vp, c_float, c_ull, c_float, c_ull, c_float, c_float, c_ull, c_float,
+                                        c_ull, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_int, c_vp]),
 }
 
 

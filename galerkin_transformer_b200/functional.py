@@ -6,6 +6,7 @@ streams and the autograd graph only.  Backward runs on PyTorch's autograd thread
 library is re-entrant and takes the device ordinal on every call.
 """
 import contextlib
+import ctypes
 import os
 import math
 import threading
@@ -17,9 +18,15 @@ from ._lib import HeadOperand, check, ptr, stream_of, workspace, require_cuda_f3
 
 ACT = {"none": 0, None: 0, "identity": 0, "relu": 1, "silu": 2}
 
-# GEMM arithmetic: "tf32" = tcgen05 tensor cores (fp32 storage, TF32 multiplies, fp32 accumulate);
-# "fp32" = exact-fp32 SIMT FMAs everywhere (the precise mode used by the tight parity tests).
-_PRECISION = "tf32"
+# GEMM arithmetic (fp32 storage everywhere):
+#   "x3"   (default) error-compensated split: the fused encoder-layer kernels run every product as three bf16 tensor-core
+#          products (a_hi b_hi + a_hi b_lo + a_lo b_hi, fp32 accumulate: ~2^-17 per product); weight-gradient GEMMs
+#          (sums over all tokens, where TF32 rounding averages out: measured 5e-6) run single-pass TF32 on tcgen05;
+#          anything not covered by a fused kernel falls back to exact fp32 FMAs.  Meets the stated fp32 parity
+#          tolerances.
+#   "tf32" every GEMM single-pass TF32 on tcgen05 (fastest unfused path; ~1e-2 gradient error through 10 layers)
+#   "fp32" exact-fp32 SIMT FMAs everywhere (the precise mode used by the tight parity tests).
+_PRECISION = "x3"
 # fold the K,V per-head LayerNorm statistics into the Q|K|V projection's tcgen05 epilogue (A/B switch)
 # -- measured 0.17 ms/step SLOWER at C3 than the separate coalesced headnorm kernel (the epilogue runs on 4 warps per
 # CTA, the stand-alone kernel on the whole GPU), so it is opt-in: GB200_FUSE_HEADNORM=1
@@ -27,9 +34,9 @@ _FUSE_HEADNORM = __import__("os").environ.get("GB200_FUSE_HEADNORM", "0") == "1"
 
 
 def set_precision(mode):
-    """'tf32' (default, tensor cores) or 'fp32' (exact SIMT path)."""
+    """'x3' (default: bf16x3 fused kernels + TF32 weight gradients), 'tf32' or 'fp32' (exact SIMT path)."""
     global _PRECISION
-    assert mode in ("tf32", "fp32")
+    assert mode in ("x3", "tf32", "fp32")
     _PRECISION = mode
 
 
@@ -160,14 +167,16 @@ class _Fork:
 # ------------------------------------------------------------------------------------------
 def gemm(A, B, C, M, N, K, *, lda, ldb, ldc, transA=False, transB=False, alpha=1.0, bias=None, act=0,
          zout=None, ldz=0, drop_p=0.0, seed=0, residual=None, ldr=0, rscale=1.0, accumulate=False,
-         ksplit=None, a_off=0, b_off=0, c_off=0, gate=None, ldg=0, gate_act=0):
+         ksplit=None, a_off=0, b_off=0, c_off=0, gate=None, ldg=0, gate_act=0, wgrad=False):
     """C = R + rscale*drop(act(alpha*op(A).op(B)+bias)); offsets are in floats.
-    gate (with gate_act relu|silu): C = rscale*drop((alpha*op(A).op(B)) * act'(gate)) -- no bias/act/residual."""
+    gate (with gate_act relu|silu): C = rscale*drop((alpha*op(A).op(B)) * act'(gate)) -- no bias/act/residual.
+    wgrad: a weight-gradient GEMM (contraction over all tokens): single-pass TF32 also in 'x3' mode."""
     lib = _lib.load()
     pa, pb = ptr(A) + 4 * a_off, ptr(B) + 4 * b_off
     nbytes = 4.0 * (M * K + K * N + M * N * (1 + (residual is not None) + (zout is not None) + (gate is not None)))
     lay = ("t" if transA else "n") + ("t" if transB else "n")
-    use_tc = _PRECISION == "tf32" and lib.gb200_gemm_tc_supported(pa, lda, pb, ldb, M, N, K)
+    use_tc = (_PRECISION == "tf32" or (_PRECISION == "x3" and wgrad)) \
+        and lib.gb200_gemm_tc_supported(pa, lda, pb, ldb, M, N, K)
     if gate is not None:
         assert bias is None and act == 0 and zout is None and residual is None and not accumulate
         if ksplit is None:
@@ -300,7 +309,7 @@ class _LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = torch.empty_like(weight)
             with fork.side(0):
-                gemm(g, x, dw, N, K, M, lda=N, ldb=K, ldc=K, transA=True)
+                gemm(g, x, dw, N, K, M, lda=N, ldb=K, ldc=K, transA=True, wgrad=True)
         if want_db:
             db = torch.empty(N, dtype=torch.float32, device=x.device)
             with fork.side(1):
@@ -370,7 +379,7 @@ class _MLP2Fn(torch.autograd.Function):
         if ctx.needs_input_grad[3]:
             dw2 = torch.empty_like(w2)
             with fork.side(0):
-                gemm(g2, h, dw2, N2, N1, M, lda=N2, ldb=N1, ldc=N1, transA=True)
+                gemm(g2, h, dw2, N2, N1, M, lda=N2, ldb=N1, ldc=N1, transA=True, wgrad=True)
         # g1 = (g2 W2) * act'(.) * mask1: ReLU gates on the stored (post-dropout) output, SiLU on the pre-activation
         g1 = torch.empty_like(h)
         if act == ACT["none"] and p1 == 0.0:
@@ -385,7 +394,7 @@ class _MLP2Fn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw1 = torch.empty_like(w1)
             with fork.side(0):
-                gemm(g1, x, dw1, N1, K, M, lda=N1, ldb=K, ldc=K, transA=True)
+                gemm(g1, x, dw1, N1, K, M, lda=N1, ldb=K, ldc=K, transA=True, wgrad=True)
         if has_b1 and ctx.needs_input_grad[2]:
             db1 = torch.empty(N1, dtype=torch.float32, device=dy.device)
             with fork.side(1):
@@ -455,8 +464,8 @@ class _LinearCatFn(torch.autograd.Function):
             dw1 = torch.empty_like(w1)
             dw2 = torch.empty_like(w2)
             with fork.side(0):
-                gemm(dy, x1, dw1, N, K1, M, lda=N, ldb=K1, ldc=K1, transA=True)
-                gemm(dy, x2, dw2, N, K2, M, lda=N, ldb=K2, ldc=K2, transA=True)
+                gemm(dy, x1, dw1, N, K1, M, lda=N, ldb=K1, ldc=K1, transA=True, wgrad=True)
+                gemm(dy, x2, dw2, N, K2, M, lda=N, ldb=K2, ldc=K2, transA=True, wgrad=True)
         if ctx.has_bias and ctx.needs_input_grad[3]:
             db = torch.empty(N, dtype=torch.float32, device=dy.device)
             with fork.side(1):
@@ -723,7 +732,7 @@ class _LinearAttentionFn(torch.autograd.Function):
         dq = dk_ = dv = None
         if self_attn:
             with fork.side(0):
-                gemm(dqkv, xs[0], dwqkv, 3 * dm, dm, T, lda=3 * dm, ldb=dm, ldc=dm, transA=True)
+                gemm(dqkv, xs[0], dwqkv, 3 * dm, dm, T, lda=3 * dm, ldb=dm, ldc=dm, transA=True, wgrad=True)
             if ctx.needs_input_grad[0]:
                 dq = torch.empty_like(query)
                 gemm(dqkv, wqkv, dq, T, dm, 3 * dm, lda=3 * dm, ldb=dm, ldc=dm)
@@ -731,7 +740,7 @@ class _LinearAttentionFn(torch.autograd.Function):
             with fork.side(0):
                 for i in range(3):
                     gemm(dqkv, xs[i], dwqkv, dm, dm, T, lda=3 * dm, ldb=dm, ldc=dm, transA=True, a_off=i * dm,
-                         c_off=i * dm * dm)
+                         c_off=i * dm * dm, wgrad=True)
             grads = []
             for i in range(3):
                 gi = None
@@ -774,6 +783,128 @@ def linear_attention(query, key, value, pos, flat, has_norm, keep_mask, *, n_hea
     pos_c = None if pos is None else pos.contiguous()
     return _LinearAttentionFn.apply(query.contiguous(), key.contiguous(), value.contiguous(), pos_c, flat, keep_mask,
                                     cfg)
+
+
+# ------------------------------------------------------------------------------------------
+# Fused encoder layer (csrc/encoder_fwd.cu): three tcgen05 kernels per layer forward
+# ------------------------------------------------------------------------------------------
+class _Ctx:
+    """stand-in autograd context for calling another Function's backward on explicit tensors"""
+
+    def __init__(self, saved, cfg, needs):
+        self.saved_tensors, self.cfg, self.needs_input_grad = saved, cfg, needs
+
+
+def encoder_fused_supported(d_model, n_head, pos_dim, d_ff):
+    return bool(_lib.load().gb200_encoder_supported(int(d_model), int(n_head), int(pos_dim), int(d_ff)))
+
+
+def _encoder_params_struct(params, H, dm, p, dff):
+    (wq, wk, wv, bq, bk, bv, *rest) = params
+    P = _lib.EncoderParams()
+    P.wq, P.wk, P.wv, P.bq, P.bk, P.bv = (ptr(t) for t in (wq, wk, wv, bq, bk, bv))
+    has_norm = len(rest) == 4 * H + 6
+    if has_norm:
+        for h in range(H):
+            P.gamma_k[h], P.beta_k[h] = ptr(rest[h]), ptr(rest[H + h])
+            P.gamma_v[h], P.beta_v[h] = ptr(rest[2 * H + h]), ptr(rest[3 * H + h])
+        rest = rest[4 * H:]
+    P.wfc, P.bfc, P.w1, P.b1, P.w2, P.b2 = (ptr(t) for t in rest)
+    P.d_model, P.n_head, P.pos_dim, P.d_ff = dm, H, p, dff
+    return P, has_norm
+
+
+class _EncoderLayerFn(torch.autograd.Function):
+    """One Galerkin encoder layer (libs/model.py:104-140) as ONE autograd node.
+
+    params = (Wq, Wk, Wv, bq, bk, bv, [gamma_K x H, beta_K x H, gamma_V x H, beta_V x H,] W_fc, b_fc, W1, b1, W2, b2)
+    forward : gb200_encoder_pack + gb200_encoder_layer_fwd (3 kernels)
+    backward: the per-operator backward launches on the tensors the fused forward saved (same layouts, same Philox
+              streams), see _LinearAttentionFn / _LinearFn / _MLP2Fn."""
+
+    @staticmethod
+    def forward(ctx, x, pos, keep_mask, cfg, *params):
+        (H, p, eps, scale, mask_p, mask_seed, p1, seed1, sign, pf, seedf, p2, seed2) = cfg
+        require_cuda_f32(x, pos, *params)
+        lib = _lib.load()
+        B, n, dm = x.shape
+        dk, d = dm // H, dm // H + p
+        dff = params[-4].shape[0]
+        T = B * n
+        dev, st = _dev(x), stream_of(x)
+        P, has_norm = _encoder_params_struct(params, H, dm, p, dff)
+        packed = torch.empty(lib.gb200_encoder_pack_bytes(dm, H, p, dff), dtype=torch.uint8, device=x.device)
+        _launch("encoder_pack", 0.0, 2.0 * packed.numel(), lib.gb200_encoder_pack, dev, ctypes.byref(P), ptr(packed), st)
+        f32 = dict(dtype=torch.float32, device=x.device)
+        qkv = torch.empty((T, 3 * dm), **f32)
+        rstd = [torch.empty((T, H), **f32) for _ in range(2)] if has_norm else [None, None]
+        A = torch.empty((B, H, d, d), **f32)
+        heads = torch.empty((B, n, H * d), **f32)
+        x1 = torch.empty((T, dm), **f32)
+        hid = torch.empty((T, dff), **f32)
+        x2 = torch.empty((B, n, dm), **f32)
+        wsb = lib.gb200_encoder_workspace_bytes(B, n, H, dk, p)
+        ws = workspace(wsb, x)
+        gflop = 2.0 * T * (3 * dm * dm + H * d * dm + 2 * dm * dff) + 4.0 * B * H * n * d * d
+        nbytes = 4.0 * T * (2 * dm + 3 * dm + H * d + dm + dff) + 2.0 * packed.numel()
+        _launch("encoder_layer_fwd", gflop, nbytes, lib.gb200_encoder_layer_fwd, dev, ptr(packed), dm, H, p, dff, ptr(x),
+                ptr(pos), B, n, int(has_norm), eps, scale, ptr(keep_mask), mask_p, mask_seed, p1, seed1, sign, pf, seedf,
+                p2, seed2, ptr(qkv), ptr(rstd[0]), ptr(rstd[1]), ptr(A), ptr(heads), ptr(x1), ptr(hid), ptr(x2), ptr(ws),
+                wsb, 7, st)
+        ctx.save_for_backward(x, pos, keep_mask, qkv, A, heads, x1, hid, packed, *[r for r in rstd if r is not None],
+                              *params)
+        ctx.cfg = cfg
+        ctx.has_norm = has_norm
+        ctx.set_materialize_grads(False)
+        return x2, A
+
+    @staticmethod
+    def backward(ctx, dy, dA_ext):
+        (x, pos, keep_mask, qkv, A, heads, x1, hid, packed, *rest) = ctx.saved_tensors
+        (H, p, eps, scale, mask_p, mask_seed, p1, seed1, sign, pf, seedf, p2, seed2) = ctx.cfg
+        has_norm = ctx.has_norm
+        rstd = rest[:2] if has_norm else []
+        params = rest[2:] if has_norm else rest
+        B, n, dm = x.shape
+        dk = dm // H
+        T = B * n
+        wfc, bfc, w1, b1, w2, b2 = params[-6:]
+        if dy is None:
+            dy = torch.zeros_like(x)
+        dy2 = dy.reshape(T, dm).contiguous()
+        # FeedForward + shortcut
+        c = _Ctx((x1, w1, w2, hid, None), (ACT["relu"], pf, seedf, p2, seed2, 1.0, True, True, True), (True,) * 12)
+        dx1, dw1, db1, dw2, db2 = _MLP2Fn.backward(c, dy2)[:5]
+        # fc + residual
+        c = _Ctx((heads.reshape(T, -1), wfc, None, None), (0, sign, p1, seed1, True, True), (True,) * 8)
+        dheads, dwfc, dbfc, dres = _LinearFn.backward(c, dx1)[:4]
+        # attention core + per-head LayerNorm + Q/K/V projection
+        flat = pack([t for t in params[:6]] + [t for t in params[6:-6]]).detach()
+        acfg = (H, dk, p, eps, "kv" if has_norm else None, scale, True, mask_p, mask_seed, False, False)
+        c = _Ctx((x, x, x, pos, flat, keep_mask, qkv, A, *rstd), acfg, (ctx.needs_input_grad[0],) + (False,) * 6)
+        dq, _, _, _, dflat, _, _ = _LinearAttentionFn.backward(c, dheads.view(B, n, -1), dA_ext)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = dq + dres.view(B, n, dm)
+        o = 3 * dm * dm
+        grads = [dflat[i * dm * dm:(i + 1) * dm * dm].view(dm, dm) for i in range(3)]
+        grads += [dflat[o + i * dm:o + (i + 1) * dm] for i in range(3)]
+        o += 3 * dm
+        if has_norm:
+            grads += [dflat[o + i * dk:o + (i + 1) * dk] for i in range(4 * H)]
+        grads += [dwfc, dbfc, dw1, db1, dw2, db2]
+        return (dx, None, None, None, *grads)
+
+
+def encoder_layer(x, pos, params, *, n_head, pos_dim, eps, attention_scale, keep_mask=None, mask_p=0.0,
+                  p_attn_out=0.0, res_sign=1.0, p_ffn=0.0, p_out=0.0):
+    """Fused Galerkin encoder layer; returns (x_out (B, n, d_model), attention matrix (B, H, d, d))."""
+    mask_p = 0.0 if keep_mask is not None else float(mask_p)
+    cfg = (int(n_head), int(pos_dim), float(eps), float(attention_scale), mask_p,
+           next_seed() if mask_p > 0.0 else 0, float(p_attn_out), next_seed() if p_attn_out > 0.0 else 0,
+           float(res_sign), float(p_ffn), next_seed() if p_ffn > 0.0 else 0, float(p_out),
+           next_seed() if p_out > 0.0 else 0)
+    return _EncoderLayerFn.apply(x.contiguous(), pos.contiguous(), keep_mask, cfg, *params)
 
 
 # ------------------------------------------------------------------------------------------
@@ -937,7 +1068,7 @@ class _SpectralConvFn(torch.autograd.Function):
                 gemm(gz, wl, dx, P, Ci, Co, lda=Co, ldb=Ci, ldc=Ci)
         if ctx.needs_input_grad[2]:
             dwl = torch.empty_like(wl)
-            gemm(gz, x, dwl, Co, Ci, P, lda=Co, ldb=Ci, ldc=Ci, transA=True)
+            gemm(gz, x, dwl, Co, Ci, P, lda=Co, ldb=Ci, ldc=Ci, transA=True, wgrad=True)
         if dbl is None and has_bias and ctx.needs_input_grad[3]:
             dbl = torch.empty(Co, dtype=torch.float32, device=x.device)
             colsum(gz, P, Co, Co, dbl)

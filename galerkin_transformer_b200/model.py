@@ -88,6 +88,8 @@ class SimpleTransformerEncoderLayer(nn.Module):
         p1 = self.dropout1.p if self.training else 0.0
         p2 = self.dropout2.p if self.training else 0.0
         sign = 1.0 if (self.residual_type in ['add', 'plus'] or self.residual_type is None) else -1.0
+        if self._fused_ok(x, pos, weight):
+            return self._forward_fused(x, pos, p1, p2, sign)
         if use_pos:
             # attention core, then  x +/- dropout1(fc(heads))  in the fc GEMM's epilogue
             heads, attn_weight = a.forward_heads(x, x, x, pos=pos, weight=weight)
@@ -105,6 +107,49 @@ class SimpleTransformerEncoderLayer(nn.Module):
         if self.attn_weight:
             return x, attn_weight
         return x
+
+
+    # ---- fused path: the whole layer as three tcgen05 kernels (csrc/encoder_fwd.cu) ----
+    def _fused_ok(self, x, pos, weight):
+        a = self.attn
+        if GF.get_precision() != 'x3' or weight is not None or self.add_layer_norm or a.attention_type != 'galerkin':
+            return False
+        if a.pos_dim < 1 or pos is None:       # without position columns the reference layer has no `fc` at all
+            return False
+        if self.ff.act_name != 'relu' or self.ff.lr2.out_features != self.d_model or x.dim() != 3 or not x.is_cuda:
+            return False
+        return GF.encoder_fused_supported(self.d_model, self.n_head, a.pos_dim, self.ff.lr1.out_features)
+
+    def _fused_params(self):
+        a = self.attn
+        ps = [lin.weight for lin in a.linears] + [lin.bias for lin in a.linears]
+        if a.add_norm:
+            for mods, attr in ((a.norm_K, "weight"), (a.norm_K, "bias"), (a.norm_V, "weight"), (a.norm_V, "bias")):
+                ps += [getattr(m, attr) for m in mods]
+        ps += [a.fc.weight, a.fc.bias]
+        return ps + [self.ff.lr1.weight, self.ff.lr1.bias, self.ff.lr2.weight, self.ff.lr2.bias]
+
+    def _forward_fused(self, x, pos, p1, p2, sign):
+        a = self.attn
+        bsz, n = x.size(0), x.size(1)
+        assert pos.size(-1) == a.pos_dim
+        d = a.d_k + a.pos_dim
+        keep = a._next_mask
+        a._next_mask = None
+        mask_p = 0.0
+        if keep is None and a.attn_dropout == 'reference':
+            mask_p = 0.5
+        elif keep is not None:
+            assert tuple(keep.shape) == (bsz, a.n_head, d, d), f"keep-mask shape {tuple(keep.shape)}"
+            keep = keep.to(device=x.device, dtype=torch.uint8).contiguous()
+        pf = self.ff.dropout.p if self.training else 0.0
+        y, attn_weight = GF.encoder_layer(x, pos, self._fused_params(), n_head=a.n_head, pos_dim=a.pos_dim, eps=a.eps,
+                                          attention_scale=1.0 / n, keep_mask=keep, mask_p=mask_p, p_attn_out=p1,
+                                          res_sign=sign, p_ffn=pf, p_out=p2)
+        a.attn_weight = attn_weight
+        if self.attn_weight:
+            return y, attn_weight
+        return y
 
 
 class PointwiseRegressor(nn.Module):

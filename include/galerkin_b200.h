@@ -244,6 +244,49 @@ int gb200_interp_bilinear_fwd(int device, const float* in, int B, int Hin, int W
 int gb200_interp_bilinear_bwd(int device, const float* dout, int B, int Hin, int Win, int C, float* din, int Hout,
                               int Wout, void* stream);
 
+/* ------------------------------------------------------------------ fused encoder layer --------
+ * SimpleTransformerEncoderLayer.forward (libs/model.py:104-140) = SimpleAttention.forward (libs/layers.py:829-899:
+ * Q/K/V projections :837-839, per-head LayerNorm loop :846-851, position concat :869-874, K^T V / n + dropout + Q.(.)
+ * :723-733, head merge + fc :892-897) + residual (:124-127) + FeedForward (libs/layers.py:979-987) + residual (:131-132),
+ * Galerkin type, as three tcgen05 kernels per 128-token tile (csrc/encoder_fwd.cu):
+ *     1. x -> [Q | LN(K) | LN(V)] and the tile's partial K~^T V~ (the LayerNorm is fused into the first of the two
+ *        back-to-back contractions; both run on TMA-staged tiles and tcgen05.mma with TMEM accumulators)
+ *     2. A = mask * sum(partials) * scale ; heads = Q~ A ; x1 = x + sign * dropout(heads W_fc^T + b_fc)
+ *     3. x2 = x1 + dropout( dropout(relu(x1 W1^T + b1)) W2^T + b2 )       (hidden tile never leaves the SM)
+ * Arithmetic: "bf16x3" -- every product is a_hi.b_hi + a_hi.b_lo + a_lo.b_hi with (hi, lo) the two-term bf16 split of
+ * the fp32 operand, fp32 accumulation: ~2^-17 relative error per product, 30x tighter than TF32.
+ * Supported shape: d_model 128, 4 heads, d_ff 256, pos_dim <= 2 (BASELINE config 3); gb200_encoder_supported() says so
+ * and the Python layer falls back to the per-operator kernels otherwise.
+ *
+ * gb200_encoder_pack: once per step, parameters -> bf16 (hi, lo) operand tile images in streaming order for the
+ * forward and backward kernels plus one fp32 block of biases / LayerNorm tables (`packed`: 128-byte aligned,
+ * gb200_encoder_pack_bytes() bytes).  Buffers saved by _fwd are exactly those the per-operator backward consumes:
+ * qkv (B n, 3 d_model) = [Q | x^_K | x^_V], rstd_k / rstd_v (B n, heads), attn (B, heads, d, d), heads (B n, heads d),
+ * x1 (B n, d_model), hidden (B n, d_ff) post-ReLU post-dropout, x2 (B n, d_model).  Dropout masks are Philox streams
+ * keyed exactly like the unfused epilogues (seed, flat element index), so either backward regenerates them.
+ * `stages`: bit 0/1/2 = run kernel 1/2/3 (7 = whole layer; tests run them one at a time). */
+#define GB200_ENC_TILES 70
+#define GB200_ENC_MAX_HEADS 8
+typedef struct gb200_encoder_params {
+    const float *wq, *wk, *wv, *bq, *bk, *bv;                 /* attn.linears.{0,1,2} */
+    const float *gamma_k[GB200_ENC_MAX_HEADS], *beta_k[GB200_ENC_MAX_HEADS];   /* attn.norm_K.{h}; NULL without norm */
+    const float *gamma_v[GB200_ENC_MAX_HEADS], *beta_v[GB200_ENC_MAX_HEADS];   /* attn.norm_V.{h} */
+    const float *wfc, *bfc;                                   /* attn.fc (d_model, d_model + heads * pos_dim) */
+    const float *w1, *b1, *w2, *b2;                           /* ff.lr1, ff.lr2 */
+    int d_model, n_head, pos_dim, d_ff;
+} gb200_encoder_params;
+int gb200_encoder_supported(int d_model, int n_head, int pos_dim, int d_ff);
+size_t gb200_encoder_pack_bytes(int d_model, int n_head, int pos_dim, int d_ff);
+int gb200_encoder_pack(int device, const gb200_encoder_params* params, void* packed, void* stream);
+size_t gb200_encoder_workspace_bytes(int B, int n, int n_head, int d_k, int pos_dim);
+int gb200_encoder_layer_fwd(int device, const void* packed, int d_model, int n_head, int pos_dim, int d_ff,
+                            const float* x, const float* pos, int B, int n, int has_norm, float eps, float attn_scale,
+                            const unsigned char* keep_mask, float mask_p, unsigned long long mask_seed,
+                            float p_attn_out, unsigned long long seed_attn_out, float res_sign, float p_ffn,
+                            unsigned long long seed_ffn, float p_out, unsigned long long seed_out, float* qkv,
+                            float* rstd_k, float* rstd_v, float* attn, float* heads, float* x1, float* hidden, float* x2,
+                            float* workspace, size_t workspace_bytes, int stages, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -418,8 +418,10 @@ def test_spectral_conv_forward_backward(shape, Co, m, act, prec):
     pd = [t.detach().clone().requires_grad_(True) for t in params]
     yr = _sc_ref(pd[0], pd[1], pd[2], pd[3], pd[4] if two_d else None, m, act, two_d)
     gr = torch.autograd.grad((yr * cot.double()).sum(), pd)
-    if act == "relu" and prec == "tf32":       # align the ReLU gate (see test_linear_autograd_tensor_cores)
-        return
     assert rel_l2(y, yr) < ftol
+    if act == "relu" and prec == "tf32":
+        # a reduced-precision pre-activation flips the ReLU gate of the few entries with |z| ~ 1e-3 |z|_rms; each flip
+        # moves one gradient entry by O(1), so the gradient bound is looser here (and only here)
+        gtol = 3e-2
     for g, r in zip(grads, gr):
         assert rel_l2(g, r) < gtol
