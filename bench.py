@@ -246,7 +246,9 @@ def main():
     ap.add_argument("--no-parts", action="store_true", help="skip the encoder-only / decoder-only timings")
     ap.add_argument("--batch-streams", type=int, default=int(os.environ.get("GB200_BATCH_STREAMS", "1")),
                     help="split the per-GPU batch into this many concurrent micro-batch chains inside the graph")
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--precision", default="x3", choices=["x3", "tf32", "fp32"],
+                    help="x3 (default): bf16x3 fused encoder kernels + TF32 weight gradients + exact fp32 elsewhere; "
+                         "tf32: every GEMM single-pass TF32; fp32: exact SIMT")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

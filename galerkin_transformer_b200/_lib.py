@@ -104,6 +104,7 @@ SIGNATURES = {
     "gb200_spectral_yidft_epilogue": (c_int, [c_int, c_vp, c_ll, c_int, c_int, c_int, c_vp, c_float, c_int,
                                               c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp]),
     "gb200_encoder_supported": (c_int, [c_int] * 4),
+    "gb200_encoder_set_trace": (c_int, [c_vp]),
     "gb200_encoder_pack_bytes": (c_sz, [c_int] * 4),
     "gb200_encoder_pack": (c_int, [c_int, _ENCP, c_vp, c_vp]),
     "gb200_encoder_workspace_bytes": (c_sz, [c_int] * 5),

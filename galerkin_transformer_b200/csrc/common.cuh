@@ -79,16 +79,19 @@ __device__ __forceinline__ float act_grad(int act, float z) {
     return 1.f;
 }
 
-// ---- counter-based RNG for fused dropout: Philox4x32-10 keyed by (seed, element index) -----
-// The same (seed, index) reproduces the same keep decision in forward and backward, so no
-// mask tensor ever touches HBM.
+// ---- counter-based RNG for fused dropout: Philox4x32-7 keyed by (seed, element index / 8) ------
+// One Philox block yields eight 16-bit uniforms, one per element: element idx uses halfword (idx & 7) of block
+// (idx >> 3).  The same (seed, index) reproduces the same keep decision in forward and backward, so no mask tensor ever
+// touches HBM.  Seven rounds are the Crush-resistant minimum of Salmon et al. (SC'11); the drop probability is quantised
+// to thr / 65536 and the keep scale is its exact inverse complement 65536 / (65536 - thr), so the mask stays unbiased
+// (p = 0.5 -> scale exactly 2, as libs/layers.py:730-731 needs).
 __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
 
 __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t idx) {
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     uint32_t c0 = (uint32_t)idx, c1 = (uint32_t)(idx >> 32), c2 = 0x9E3779B9u, c3 = 0xBB67AE85u;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < 7; ++r) {
         const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
         uint32_t h0 = mulhi32(M0, c0), l0 = M0 * c0;
         uint32_t h1 = mulhi32(M1, c2), l1 = M1 * c2;
@@ -98,14 +101,29 @@ __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t idx) {
     }
     return make_uint4(c0, c1, c2, c3);
 }
+__device__ __forceinline__ uint32_t dropout_threshold(float p) { return (uint32_t)(p * 65536.f + 0.5f); }
+__device__ __forceinline__ float dropout_keep_scale(uint32_t thr) { return 65536.f / (65536.f - (float)thr); }
 
 // keep-scale for element `idx`: 0 if dropped, 1/(1-p) if kept.  p in [0,1).
 __device__ __forceinline__ float dropout_scale(float p, uint64_t seed, uint64_t idx) {
     if (p <= 0.f) return 1.f;
-    uint4 r = philox4x32(seed, idx >> 2);
-    uint32_t u = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
-    float uf = (float)(u >> 8) * (1.0f / 16777216.0f);       // [0,1)
-    return uf < p ? 0.f : 1.f / (1.f - p);
+    const uint4 r = philox4x32(seed, idx >> 3);
+    const uint32_t e = (uint32_t)idx & 7u;
+    const uint32_t w = (e >> 1) == 0 ? r.x : (e >> 1) == 1 ? r.y : (e >> 1) == 2 ? r.z : r.w;
+    const uint32_t u = (e & 1u) ? (w >> 16) : (w & 0xffffu);
+    const uint32_t thr = dropout_threshold(p);
+    return u < thr ? 0.f : dropout_keep_scale(thr);
+}
+
+// eight consecutive elements idx..idx+7 (idx % 8 == 0) from ONE Philox block -- same stream as dropout_scale
+__device__ __forceinline__ void dropout_scale8(float p, uint64_t seed, uint64_t idx, float (&s)[8]) {
+    const uint4 r = philox4x32(seed, idx >> 3);
+    const uint32_t thr = dropout_threshold(p);
+    const float keep = dropout_keep_scale(thr);
+    s[0] = (r.x & 0xffffu) < thr ? 0.f : keep; s[1] = (r.x >> 16) < thr ? 0.f : keep;
+    s[2] = (r.y & 0xffffu) < thr ? 0.f : keep; s[3] = (r.y >> 16) < thr ? 0.f : keep;
+    s[4] = (r.z & 0xffffu) < thr ? 0.f : keep; s[5] = (r.z >> 16) < thr ? 0.f : keep;
+    s[6] = (r.w & 0xffffu) < thr ? 0.f : keep; s[7] = (r.w >> 16) < thr ? 0.f : keep;
 }
 
 // out[c] (+)= scale * sum_{p < nparts} part[p * stride + c]   for c < width: a (32 x 32)-thread CTA per 32
@@ -129,12 +147,14 @@ __device__ __forceinline__ void reduce_partials_2d(const float* __restrict__ par
     }
 }
 
-// four consecutive elements idx..idx+3 (idx % 4 == 0) from ONE Philox block -- same stream as dropout_scale
+// four consecutive elements idx..idx+3 (idx % 4 == 0): half a Philox block -- same stream as dropout_scale
 __device__ __forceinline__ float4 dropout_scale4(float p, uint64_t seed, uint64_t idx) {
-    const uint4 r = philox4x32(seed, idx >> 2);
-    const float keep = 1.f / (1.f - p), k = 1.0f / 16777216.0f;
-    return make_float4((float)(r.x >> 8) * k < p ? 0.f : keep, (float)(r.y >> 8) * k < p ? 0.f : keep,
-                       (float)(r.z >> 8) * k < p ? 0.f : keep, (float)(r.w >> 8) * k < p ? 0.f : keep);
+    const uint4 r = philox4x32(seed, idx >> 3);
+    const uint32_t thr = dropout_threshold(p);
+    const float keep = dropout_keep_scale(thr);
+    const uint32_t w0 = (idx & 4) ? r.z : r.x, w1 = (idx & 4) ? r.w : r.y;
+    return make_float4((w0 & 0xffffu) < thr ? 0.f : keep, (w0 >> 16) < thr ? 0.f : keep,
+                       (w1 & 0xffffu) < thr ? 0.f : keep, (w1 >> 16) < thr ? 0.f : keep);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -58,6 +58,18 @@ __device__ __forceinline__ uint32_t idesc_bf16(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
 __device__ __forceinline__ uint64_t kdesc(uint32_t smem_addr) { return umma_desc<2>(smem_addr, 16, 1024); }
+// MN-major operand (contraction over the ROWS of a chunk image: rows = K index, 128-byte rows = 64 MN elements):
+// 8-row groups 1024 B apart (SBO), 64-wide MN blocks `lbo` bytes apart; one k-step = 16 rows = 2048 B.  The byte image
+// is the same as a K-major chunk, so one tile can feed both kinds of contraction.
+__device__ __forceinline__ uint64_t mndesc(uint32_t smem_addr, uint32_t lbo) { return umma_desc<2>(smem_addr, lbo, 1024); }
+__device__ __forceinline__ uint32_t idesc_bf16_mn(int n) { return idesc_bf16(n) | (1u << 15) | (1u << 16); }
+// three products of one k-step, both operands MN-major
+__device__ __forceinline__ void mma3_mn(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t lbo_a, uint32_t b_hi, uint32_t b_lo,
+                                        uint32_t lbo_b, uint32_t idesc, bool first) {
+    tc_mma_bf16(d, mndesc(a_hi, lbo_a), mndesc(b_hi, lbo_b), idesc, first ? 0u : 1u);
+    tc_mma_bf16(d, mndesc(a_hi, lbo_a), mndesc(b_lo, lbo_b), idesc, 1u);
+    tc_mma_bf16(d, mndesc(a_lo, lbo_a), mndesc(b_hi, lbo_b), idesc, 1u);
+}
 
 // the three products of one 16-wide k-step (a_* / b_* are shared-memory byte addresses of the k-step)
 __device__ __forceinline__ void mma3(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
@@ -177,6 +189,30 @@ __device__ __forceinline__ void warp_store_block(float* stage, const float (&v)[
     }
     __syncwarp();
 }
+// [32 x 34] block (one head of the head-merged attention output, 136-byte row segments): lanes take consecutive float2
+// of the staged block, so one store instruction covers ~2 rows instead of 32 scattered words
+__device__ __forceinline__ void warp_store_rows34(float* stage, const float (&v)[32], float e0, float e1, int lane,
+                                                  float* g, long long ld, int nrows, int width) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(&stage[lane * STAGE_PITCH + j]) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    *reinterpret_cast<float2*>(&stage[lane * STAGE_PITCH + 32]) = make_float2(e0, e1);
+    __syncwarp();
+    if ((width & 1) == 0) {
+        const int w2 = width >> 1;
+        for (int f = lane; f < 32 * w2; f += 32) {
+            const int r = f / w2, c = (f - r * w2) * 2;
+            if (r < nrows)
+                *reinterpret_cast<float2*>(g + (long long)r * ld + c) = *reinterpret_cast<const float2*>(&stage[r * STAGE_PITCH + c]);
+        }
+    } else {
+        for (int f = lane; f < 32 * width; f += 32) {
+            const int r = f / width, c = f - r * width;
+            if (r < nrows) g[(long long)r * ld + c] = stage[r * STAGE_PITCH + c];
+        }
+    }
+    __syncwarp();
+}
 __device__ __forceinline__ void warp_load_block(float* stage, float (&v)[32], int lane, const float* g, long long ld,
                                                 int nrows) {
     const int rr = lane >> 3, c4 = (lane & 7) * 4;
@@ -196,17 +232,38 @@ __device__ __forceinline__ void warp_load_block(float* stage, float (&v)[32], in
     __syncwarp();
 }
 
-// fused dropout over 32 consecutive elements of one row (first flat element index idx0, idx0 % 4 == 0): same Philox
+// fused dropout over 32 consecutive elements of one row (first flat element index idx0, idx0 % 8 == 0): same Philox
 // stream as the unfused GEMM epilogues, so a fused forward and an unfused backward agree on the mask
 __device__ __forceinline__ void dropout32(float (&v)[32], float p, unsigned long long seed, unsigned long long idx0) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-        const float4 ds = dropout_scale4(p, seed, idx0 + j);
-        v[j] *= ds.x; v[j + 1] *= ds.y; v[j + 2] *= ds.z; v[j + 3] *= ds.w;
+    for (int j = 0; j < 32; j += 8) {
+        float ds[8];
+        dropout_scale8(p, seed, idx0 + j, ds);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[j + i] *= ds[i];
     }
 }
 
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NWORK * 32) : "memory"); }
+
+// ---- diagnostics: per-CTA clock stamps (gb200_encoder_set_trace); 32 slots per CTA, slot 31 = globaltimer at entry ----
+static __device__ unsigned long long* g_enc_trace = nullptr;    // one copy per translation unit
+__device__ __forceinline__ void trace(int slot) {
+    if (g_enc_trace) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+        g_enc_trace[(size_t)blockIdx.x * 32 + slot] = t;
+    }
+}
+__device__ __forceinline__ void trace_entry() {
+    if (g_enc_trace) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_enc_trace[(size_t)blockIdx.x * 32 + 31] = t;
+    }
+}
+// 1024-aligned dynamic shared memory base that keeps the shared address space visible to the compiler (LDS / STS)
+__device__ __forceinline__ uint8_t* smem_base(uint8_t* raw) { return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u); }
 
 // ---- one-time CTA setup shared by every kernel: barriers, TMEM allocation --------------------------------------
 __device__ __forceinline__ uint32_t tmem_alloc_512(uint32_t* slot, int warp) {

@@ -48,7 +48,7 @@ constexpr int QKV_SMEM = 4 * TILE_BYTES + QKV_RING * TILE_BYTES + NWORK * STAGE_
 
 __global__ void __launch_bounds__(THREADS, 1) enc_qkv_kernel(const __grid_constant__ CUtensorMap mapX, QkvArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_base(smem_raw);
     uint8_t* X = smem;                                        // x tile, later the K~^T operand (A2)
     uint8_t* ring = smem + 4 * TILE_BYTES;                    // weight tiles, later the [V~ | pos]^T operand (B2)
     float* staging = reinterpret_cast<float*>(ring + QKV_RING * TILE_BYTES);
@@ -71,7 +71,9 @@ __global__ void __launch_bounds__(THREADS, 1) enc_qkv_kernel(const __grid_consta
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX) : "memory");
     }
+    if (threadIdx.x == 0) { trace_entry(); trace(0); }
     const uint32_t tmem = tmem_alloc_512(&bar->tmem_slot, warp);
+    if (threadIdx.x == 0) trace(1);
 
     if (warp == 0) {
         if (lane == 0) {   // ---------------- producer ----------------
@@ -82,7 +84,9 @@ __global__ void __launch_bounds__(THREADS, 1) enc_qkv_kernel(const __grid_consta
                 mbar_wait(&bar->empty[s], ((i / QKV_RING) & 1) ^ 1);
                 mbar_expect_tx(&bar->full[s], TILE_BYTES);
                 bulk_load(ring + s * TILE_BYTES, a.wtiles + (size_t)i * TILE_BYTES, TILE_BYTES, &bar->full[s]);
+                if (i == 5) trace(2);
             }
+            trace(3);
         }
     } else if (warp == 1) {
         if (lane == 0) {   // ---------------- MMA issuer ----------------
@@ -90,10 +94,12 @@ __global__ void __launch_bounds__(THREADS, 1) enc_qkv_kernel(const __grid_consta
             const uint32_t id128 = idesc_bf16(128);
             mbar_wait(&bar->xconv, 0);
             tc_fence_after();
+            trace(4);
             for (int i = 0; i < 12; ++i) {
                 const int s = i % QKV_RING;
                 mbar_wait(&bar->full[s], (i / QKV_RING) & 1);
                 tc_fence_after();
+                if (i == 0) trace(5);
                 const int nb = i >> 2, kc = (i >> 1) & 1;
                 mma_weight_tile(tmem + nb * 128, xa + (2 * kc) * TILE_BYTES, xa + (2 * kc + 1) * TILE_BYTES,
                                 rb + s * TILE_BYTES, (i & 1) == 0, id128, kc == 0);
@@ -102,20 +108,23 @@ __global__ void __launch_bounds__(THREADS, 1) enc_qkv_kernel(const __grid_consta
             }
             // second contraction, over the tile's tokens:  D2 = K~^T [V~ | pos]   (M = 128 K features, N = 144),
             //                                              D3 = V~^T pos          (M = 128 V features, N = 16)
+            trace(6);
             mbar_wait(&bar->hand[0], 0);
             tc_fence_after();
-            const uint32_t id144 = idesc_bf16(144), id16 = idesc_bf16(16);
-            constexpr uint32_t B2C = 144 * 128;                       // one [144 x 64] chunk image
+            trace(7);
+            // operands are MN-major chunk images [128 token rows][64 features]: K~ = X blocks {0: hi f<64, 1: lo f<64,
+            // 2: hi f>=64, 3: lo f>=64}; [V~ | pos] = ring blocks {hi, lo} x {f<64, f>=64, pos}
+            const uint32_t id144 = idesc_bf16_mn(144), id16 = idesc_bf16_mn(16);
 #pragma unroll
-            for (int kc = 0; kc < 2; ++kc)
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint32_t ah = xa + (2 * kc) * TILE_BYTES + ks * 32, al = ah + TILE_BYTES;
-                    const uint32_t bh = rb + (2 * kc) * B2C + ks * 32, bl = bh + B2C;
-                    mma3(tmem, ah, al, bh, bl, id144, kc == 0 && ks == 0);
-                    mma3(tmem + 144, bh, bl, bh + 128 * 128, bl + 128 * 128, id16, kc == 0 && ks == 0);
-                }
+            for (int ks = 0; ks < 8; ++ks) {
+                const uint32_t ah = xa + ks * 2048, al = ah + TILE_BYTES;
+                const uint32_t bh = rb + ks * 2048, bl = bh + TILE_BYTES;
+                mma3_mn(tmem, ah, al, 2 * TILE_BYTES, bh, bl, 2 * TILE_BYTES, id144, ks == 0);
+                mma3_mn(tmem + 144, bh, bl, 2 * TILE_BYTES, bh + 4 * TILE_BYTES, bl + 4 * TILE_BYTES, 2 * TILE_BYTES, id16,
+                        ks == 0);
+            }
             tc_commit(&bar->dfull[3]);
+            trace(8);
         }
     } else {               // ---------------- workers ----------------
         const int w = warp - 2, q = warp & 3, hf = w >> 2;
@@ -126,85 +135,105 @@ __global__ void __launch_bounds__(THREADS, 1) enc_qkv_kernel(const __grid_consta
         const int nrows = max(0, min(32, nvalid - q * 32));
         float* stage = staging + w * 32 * STAGE_PITCH;
         for (int i = wt; i < VEC_FLOATS; i += NWORK * 32) vec[i] = a.vec[i];
+        float pv[2] = {0.f, 0.f};                              // this row's position (needed late: fetched early)
+        if (valid && hf == 0) {
+            if (p > 0) pv[0] = a.pos[grow * p];
+            if (p > 1) pv[1] = a.pos[grow * p + 1];
+        }
         mbar_wait(&bar->xfull, 0);
+        if (wt == 0) trace(9);
         split_tile_inplace(X, wt & 127, wt >> 7);
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar->xconv);
         worker_bar();                                          // vec[] visible to every worker
+        if (wt == 0) trace(10);
 
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
         float v[32];
         // Q chunks of heads 2hf, 2hf+1: bias, store
         mbar_wait(&bar->dfull[0], 0);
         tc_fence_after();
+        if (wt == 0) trace(11);
         for (int hh = 0; hh < 2; ++hh) {
             const int h = 2 * hf + hh;
             tmem_ld32(tlane + h * 32, v);
+            const float4* bb = reinterpret_cast<const float4*>(vec + VEC_BQKV + h * 32);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += vec[VEC_BQKV + h * 32 + j];
+            for (int j = 0; j < 8; ++j) {
+                const float4 t = bb[j];
+                v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+            }
             warp_store_block(stage, v, lane, a.qkv + ((long long)b * a.n + t0 + q * 32) * 384 + h * 32, 384, nrows);
         }
         // every projection MMA has completed: the x tile and the weight ring may be overwritten
+        if (wt == 0) trace(12);
         mbar_wait(&bar->dfull[2], 0);
         tc_fence_after();
+        if (wt == 0) trace(13);
         uint8_t* B2 = ring;
-        constexpr uint32_t B2C = 144 * 128;
-        const int kc = row >> 6, ku = (row & 63) >> 3, kw = (row & 7) * 2;
-        for (int blk = 1; blk <= 2; ++blk) {                   // 1: K -> A2 (in X), 2: V -> B2 (in the ring)
+        for (int blk = 1; blk <= 2; ++blk) {                   // 1: K -> X blocks, 2: V -> ring blocks
             for (int hh = 0; hh < 2; ++hh) {
                 const int h = 2 * hf + hh;
                 tmem_ld32(tlane + blk * 128 + h * 32, v);
+                {
+                    const float4* bb = reinterpret_cast<const float4*>(vec + VEC_BQKV + blk * 128 + h * 32);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += vec[VEC_BQKV + blk * 128 + h * 32 + j];
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 t = bb[j];
+                        v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+                    }
+                }
                 if (a.has_norm) {
-                    float mean = 0.f;
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) mean += v[j];
-                    mean *= (1.f / 32.f);
-                    float var = 0.f;
+                    for (int j = 0; j < 32; j += 4) { s0 += v[j]; s1 += v[j + 1]; s2 += v[j + 2]; s3 += v[j + 3]; }
+                    const float mean = ((s0 + s1) + (s2 + s3)) * (1.f / 32.f);
+                    s0 = s1 = s2 = s3 = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) { v[j] -= mean; var = fmaf(v[j], v[j], var); }
-                    const float rs = rsqrtf(var * (1.f / 32.f) + a.eps);
+                    for (int j = 0; j < 32; j += 4) {
+                        v[j] -= mean; v[j + 1] -= mean; v[j + 2] -= mean; v[j + 3] -= mean;
+                        s0 = fmaf(v[j], v[j], s0); s1 = fmaf(v[j + 1], v[j + 1], s1);
+                        s2 = fmaf(v[j + 2], v[j + 2], s2); s3 = fmaf(v[j + 3], v[j + 3], s3);
+                    }
+                    const float rs = rsqrtf(((s0 + s1) + (s2 + s3)) * (1.f / 32.f) + a.eps);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] *= rs;
                     if (valid) (blk == 1 ? a.rstd_k : a.rstd_v)[grow * NH + h] = rs;
                 }
                 warp_store_block(stage, v, lane, a.qkv + ((long long)b * a.n + t0 + q * 32) * 384 + blk * 128 + h * 32,
                                  384, nrows);
-                // operand of the token contraction: affine applied, rows past the sample's end are zero
-                const float* gam = vec + (blk == 1 ? VEC_GK : VEC_GV) + h * 32;
-                const float* bet = vec + (blk == 1 ? VEC_BK : VEC_BV) + h * 32;
-                uint8_t* hi = (blk == 1) ? X + (2 * kc) * TILE_BYTES : B2 + (2 * kc) * B2C;
-                uint8_t* lo = hi + ((blk == 1) ? TILE_BYTES : B2C);
+                // operand of the token contraction: affine applied, rows past the sample's end are zero.
+                // MN-major image: row = token, head h = 4 units of MN block h / 2
+                if (a.has_norm) {
+                    const float4* gg = reinterpret_cast<const float4*>(vec + (blk == 1 ? VEC_GK : VEC_GV) + h * 32);
+                    const float4* be = reinterpret_cast<const float4*>(vec + (blk == 1 ? VEC_BK : VEC_BV) + h * 32);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float t = a.has_norm ? fmaf(v[j], gam[j], bet[j]) : v[j];
-                    if (!valid) t = 0.f;
-                    unsigned short th, tl;
-                    split1(t, th, tl);
-                    const int f = h * 32 + j;                  // operand row = feature, K index = token
-                    const uint32_t off = (uint32_t)(f * 128 + ((ku ^ (f & 7)) << 4) + kw);
-                    *reinterpret_cast<unsigned short*>(hi + off) = th;
-                    *reinterpret_cast<unsigned short*>(lo + off) = tl;
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 g4 = gg[j], b4 = be[j];
+                        v[4 * j] = fmaf(v[4 * j], g4.x, b4.x); v[4 * j + 1] = fmaf(v[4 * j + 1], g4.y, b4.y);
+                        v[4 * j + 2] = fmaf(v[4 * j + 2], g4.z, b4.z); v[4 * j + 3] = fmaf(v[4 * j + 3], g4.w, b4.w);
+                    }
                 }
+                if (!valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                }
+                uint8_t* hi = (blk == 1 ? X : B2) + (h >> 1) * 2 * TILE_BYTES;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) store_unit(hi, hi + TILE_BYTES, row, (h & 1) * 4 + u, &v[8 * u]);
+                if (wt == 0) trace(21 + (blk - 1) * 2 + hh);
             }
         }
-        if (hf == 0) {     // position rows 128..143 of B2 (zero beyond p) and this warp's share of pos^T pos
-            float pv[2] = {0.f, 0.f};
-            if (valid)
-                for (int c = 0; c < p; ++c) pv[c] = a.pos[grow * p + c];
-            uint8_t* hi = B2 + (2 * kc) * B2C;
-            uint8_t* lo = hi + B2C;
+        if (wt == 0) trace(20);
+        if (hf == 0) {     // position block of B2 (MN block 2: 16 columns, zero beyond p) and this warp's share of pos^T pos
+            float x8[16];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                unsigned short th = 0, tl = 0;
-                if (c < 2) split1(pv[c], th, tl);
-                const int f = 128 + c;
-                const uint32_t off = (uint32_t)(f * 128 + ((ku ^ (f & 7)) << 4) + kw);
-                *reinterpret_cast<unsigned short*>(hi + off) = th;
-                *reinterpret_cast<unsigned short*>(lo + off) = tl;
-            }
+            for (int c = 0; c < 16; ++c) x8[c] = 0.f;
+            x8[0] = pv[0]; x8[1] = pv[1];
+            uint8_t* hi = B2 + 4 * TILE_BYTES;
+            store_unit(hi, hi + TILE_BYTES, row, 0, &x8[0]);
+            store_unit(hi, hi + TILE_BYTES, row, 1, &x8[8]);
             const float p00 = warp_sum(pv[0] * pv[0]), p01 = warp_sum(pv[0] * pv[1]), p11 = warp_sum(pv[1] * pv[1]);
             if (lane == 0) { ppw[q * 4 + 0] = p00; ppw[q * 4 + 1] = p01; ppw[q * 4 + 2] = p01; ppw[q * 4 + 3] = p11; }
         }
@@ -212,11 +241,13 @@ __global__ void __launch_bounds__(THREADS, 1) enc_qkv_kernel(const __grid_consta
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar->hand[0]);
+        if (wt == 0) trace(14);
 
         // partial attention matrix of this tile: A_h[i][j], i/j = 0..p-1 position, p.. = feature
         mbar_wait(&bar->dfull[3], 0);
         tc_fence_after();
         worker_bar();                                          // ppw[] complete
+        if (wt == 0) trace(15);
         float* P = a.part + ((long long)(b * a.tiles + tile) * NH + q) * d * d;       // head q
         if (hf == 0) {     // rows = K features of head q: columns [V features of head q | pos]
             tmem_ld32(tlane + q * 32, v);
@@ -239,8 +270,10 @@ __global__ void __launch_bounds__(THREADS, 1) enc_qkv_kernel(const __grid_consta
             }
         }
         tc_fence_before();
+        if (wt == 0) trace(16);
     }
     tmem_free_512(tmem, warp);
+    if (threadIdx.x == 0) trace(17);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -272,7 +305,7 @@ constexpr int ATT_SMEM = ATT_R_BYTES + 19 * 1024 + ATT_RING * TILE_BYTES + NWORK
 
 __global__ void __launch_bounds__(THREADS, 1) enc_attn_kernel(const __grid_constant__ CUtensorMap mapQ, AttnArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_base(smem_raw);
     uint8_t* R = smem;                                         // Q tile | B_a  ->  heads operand
     uint8_t* BA = R + 4 * TILE_BYTES;                          // 2 chunks x (hi, lo) x [48 rows x 128 B]
     float* As = reinterpret_cast<float*>(R + ATT_R_BYTES);     // [4][d][d]
@@ -295,7 +328,9 @@ __global__ void __launch_bounds__(THREADS, 1) enc_attn_kernel(const __grid_const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapQ) : "memory");
     }
+    if (threadIdx.x == 0) { trace_entry(); trace(0); }
     const uint32_t tmem = tmem_alloc_512(&bar->tmem_slot, warp);
+    if (threadIdx.x == 0) trace(1);
     constexpr uint32_t BAC = HP * 128;                         // one [48 x 64] chunk image of B_a
     constexpr int DB_COL = 4 * HP;                             // fc accumulator columns 192..319
 
@@ -317,6 +352,7 @@ __global__ void __launch_bounds__(THREADS, 1) enc_attn_kernel(const __grid_const
             mbar_wait(&bar->xconv, 0);
             mbar_wait(&bar->hand[0], 0);
             tc_fence_after();
+            trace(4);
             // heads_h = Q_h A_h[p:, :]  (the rank-p position part is added by the epilogue): K = 32 = two k-steps
 #pragma unroll
             for (int h = 0; h < 4; ++h)
@@ -330,6 +366,7 @@ __global__ void __launch_bounds__(THREADS, 1) enc_attn_kernel(const __grid_const
             tc_commit(&bar->dfull[0]);
             mbar_wait(&bar->hand[1], 0);
             tc_fence_after();
+            trace(7);
             for (int i = 0; i < 6; ++i) {
                 const int s = i % ATT_RING;
                 mbar_wait(&bar->full[s], (i / ATT_RING) & 1);
@@ -340,12 +377,14 @@ __global__ void __launch_bounds__(THREADS, 1) enc_attn_kernel(const __grid_const
                 tc_commit(&bar->empty[s]);
             }
             tc_commit(&bar->dfull[1]);
+            trace(8);
         }
     } else {
         const int w = warp - 2, q = warp & 3, hf = w >> 2;
         const int wt = threadIdx.x - 64;
         const int row = q * 32 + lane;
         const bool valid = row < nvalid;
+        if (wt == 0) trace(9);
         const long long grow = (long long)b * a.n + t0 + row;
         const long long grow0 = (long long)b * a.n + t0 + q * 32;
         const int nrows = max(0, min(32, nvalid - q * 32));
@@ -356,18 +395,41 @@ __global__ void __launch_bounds__(THREADS, 1) enc_attn_kernel(const __grid_const
             unsigned long long mseed = a.mask_seed;
             if (a.mask_p > 0.f && a.seed_off) mseed += *a.seed_off;
             const float* pb = a.part + (long long)b * a.tiles * NH * dd;
-            for (int e = wt; e < NH * dd; e += NWORK * 32) {
-                float s = 0.f;
-                for (int k = 0; k < a.tiles; ++k) s += pb[(long long)k * NH * dd + e];
-                s *= a.scale;
-                const long long E = (long long)b * NH * dd + e;
-                if (a.keep_mask) s *= 2.f * (float)a.keep_mask[E];
-                else if (a.mask_p > 0.f) s *= dropout_scale(a.mask_p, mseed, (unsigned long long)E);
-                As[e] = s;
-                if (tile == 0) a.attn[E] = s;
+            // every thread owns <= 19 elements; the tile partials are summed in tile order (deterministic) with all of a
+            // tile's loads in flight at once
+            constexpr int EPT = (NH * 34 * 34 + NWORK * 32 - 1) / (NWORK * 32);
+            float acc[EPT];
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) acc[i] = 0.f;
+            const int ne = NH * dd;
+            for (int k = 0; k < a.tiles; k += 2) {
+                const float* p0 = pb + (long long)k * ne;
+                const bool two = k + 1 < a.tiles;
+                float t0[EPT], t1[EPT];
+#pragma unroll
+                for (int i = 0; i < EPT; ++i) {
+                    const int e = wt + i * NWORK * 32;
+                    t0[i] = e < ne ? __ldg(p0 + e) : 0.f;
+                    t1[i] = (two && e < ne) ? __ldg(p0 + ne + e) : 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < EPT; ++i) acc[i] = (acc[i] + t0[i]) + t1[i];
+            }
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) {
+                const int e = wt + i * NWORK * 32;
+                if (e < ne) {
+                    float s = acc[i] * a.scale;
+                    const long long E = (long long)b * ne + e;
+                    if (a.keep_mask) s *= 2.f * (float)a.keep_mask[E];
+                    else if (a.mask_p > 0.f) s *= dropout_scale(a.mask_p, mseed, (unsigned long long)E);
+                    As[e] = s;
+                    if (tile == 0) a.attn[E] = s;
+                }
             }
         }
         worker_bar();
+        if (wt == 0) trace(10);
         // B operand of heads_h = Q_h A_h[p:, :]:  row = output column j (48, zero past d), K = feature i of head h;
         // heads (2c, 2c+1) share chunk c (K offsets 0 and 32)
         for (int u = wt; u < 4 * HP * 4; u += NWORK * 32) {
@@ -381,11 +443,14 @@ __global__ void __launch_bounds__(THREADS, 1) enc_attn_kernel(const __grid_const
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar->hand[0]);
+        if (wt == 0) trace(11);
         mbar_wait(&bar->xfull, 0);
+        if (wt == 0) trace(12);
         split_tile_inplace(R, wt & 127, wt >> 7);
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar->xconv);
+        if (wt == 0) trace(13);
 
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
         float v[32];
@@ -394,6 +459,7 @@ __global__ void __launch_bounds__(THREADS, 1) enc_attn_kernel(const __grid_const
             for (int c = 0; c < p; ++c) pv[c] = a.pos[grow * p + c];
         mbar_wait(&bar->dfull[0], 0);                          // heads accumulators ready; Q tile and B_a are dead
         tc_fence_after();
+        if (wt == 0) trace(14);
         for (int hh = 0; hh < 2; ++hh) {
             const int h = 2 * hf + hh;
             float e0, e1;
@@ -406,12 +472,7 @@ __global__ void __launch_bounds__(THREADS, 1) enc_attn_kernel(const __grid_const
             e1 += pv[0] * A0[33] + pv[1] * A0[d + 33];
             if (d < 34) e1 = 0.f;
             if (d < 33) e0 = 0.f;
-            if (valid) {
-                float* hp = a.heads + grow * (NH * d) + h * d;
-                for (int j = 0; j < 32; ++j) hp[j] = v[j];
-                if (d > 32) hp[32] = e0;
-                if (d > 33) hp[33] = e1;
-            }
+            warp_store_rows34(stage, v, e0, e1, lane, a.heads + grow0 * (NH * d) + h * d, NH * d, nrows, d);
             // operand of the fc GEMM: K index h * 48 + j -> 16-byte units 6h .. 6h+5 of the head-padded row
             float tail[16];
 #pragma unroll
@@ -428,9 +489,11 @@ __global__ void __launch_bounds__(THREADS, 1) enc_attn_kernel(const __grid_const
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar->hand[1]);
+        if (wt == 0) trace(15);
 
         mbar_wait(&bar->dfull[1], 0);
         tc_fence_after();
+        if (wt == 0) trace(16);
         const unsigned long long seed1 = a.seed1 + ((a.p1 > 0.f && a.seed_off) ? *a.seed_off : 0ull);
         for (int cc = 0; cc < 2; ++cc) {
             const int c0 = hf * 64 + cc * 32;
@@ -445,8 +508,10 @@ __global__ void __launch_bounds__(THREADS, 1) enc_attn_kernel(const __grid_const
             warp_store_block(stage, v, lane, a.x1 + grow0 * DM + c0, DM, nrows);
         }
         tc_fence_before();
+        if (wt == 0) trace(17);
     }
     tmem_free_512(tmem, warp);
+    if (threadIdx.x == 0) trace(18);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -469,7 +534,7 @@ constexpr int FFN_SMEM = 8 * TILE_BYTES + FFN_RING * TILE_BYTES + NWORK * STAGE_
 
 __global__ void __launch_bounds__(THREADS, 1) enc_ffn_kernel(const __grid_constant__ CUtensorMap mapX, FfnArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_base(smem_raw);
     uint8_t* R = smem;                                         // x1 tile (first 4 tiles) -> hidden operand (8 tiles)
     uint8_t* ring = R + 8 * TILE_BYTES;
     float* staging = reinterpret_cast<float*>(ring + FFN_RING * TILE_BYTES);
@@ -490,7 +555,9 @@ __global__ void __launch_bounds__(THREADS, 1) enc_ffn_kernel(const __grid_consta
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX) : "memory");
     }
+    if (threadIdx.x == 0) { trace_entry(); trace(0); }
     const uint32_t tmem = tmem_alloc_512(&bar->tmem_slot, warp);
+    if (threadIdx.x == 0) trace(1);
     constexpr int DY_COL = 256;
 
     if (warp == 0) {
@@ -511,6 +578,7 @@ __global__ void __launch_bounds__(THREADS, 1) enc_ffn_kernel(const __grid_consta
             const uint32_t id128 = idesc_bf16(128);
             mbar_wait(&bar->xconv, 0);
             tc_fence_after();
+            trace(4);
             for (int i = 0; i < 8; ++i) {                      // hidden = x1 W1^T : two N blocks of 128
                 const int s = i % FFN_RING;
                 mbar_wait(&bar->full[s], (i / FFN_RING) & 1);
@@ -521,12 +589,14 @@ __global__ void __launch_bounds__(THREADS, 1) enc_ffn_kernel(const __grid_consta
                 tc_commit(&bar->empty[s]);
                 if ((i & 3) == 3) tc_commit(&bar->dfull[nb]);
             }
+            trace(5);
             for (int i = 8; i < 16; ++i) {                     // y = hidden W2^T : K chunks follow the epilogue
                 const int s = i % FFN_RING;
                 const int kc = (i - 8) >> 1;
                 if (((i - 8) & 1) == 0) {
                     mbar_wait(&bar->hand[kc], 0);
                     tc_fence_after();
+                    trace(20 + kc);
                 }
                 mbar_wait(&bar->full[s], (i / FFN_RING) & 1);
                 tc_fence_after();
@@ -535,6 +605,7 @@ __global__ void __launch_bounds__(THREADS, 1) enc_ffn_kernel(const __grid_consta
                 tc_commit(&bar->empty[s]);
             }
             tc_commit(&bar->dfull[2]);
+            trace(8);
         }
     } else {
         const int w = warp - 2, q = warp & 3, hf = w >> 2;
@@ -547,11 +618,13 @@ __global__ void __launch_bounds__(THREADS, 1) enc_ffn_kernel(const __grid_consta
         b1[wt] = a.vec[VEC_B1 + wt];
         if (wt < DM) b2[wt] = a.vec[VEC_B2 + wt];
         mbar_wait(&bar->xfull, 0);
+        if (wt == 0) trace(9);
         split_tile_inplace(R, wt & 127, wt >> 7);
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar->xconv);
         worker_bar();
+        if (wt == 0) trace(10);
 
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
         const unsigned long long so = a.seed_off ? *a.seed_off : 0ull;
@@ -559,6 +632,8 @@ __global__ void __launch_bounds__(THREADS, 1) enc_ffn_kernel(const __grid_consta
         // hidden columns hf*128 .. +127 (N block hf): bias, ReLU, dropout; saved to HBM and handed to the second GEMM
         mbar_wait(&bar->dfull[hf], 0);
         tc_fence_after();
+        if (wt == 0) trace(11);
+        if (wt == 128) trace(12);
         for (int cc = 0; cc < 4; ++cc) {
             const int c0 = hf * 128 + cc * 32;
             tmem_ld32(tlane + c0, v);
@@ -582,8 +657,11 @@ __global__ void __launch_bounds__(THREADS, 1) enc_ffn_kernel(const __grid_consta
             }
         }
         // y columns hf*64 .. +63
+        if (wt == 0) trace(13);
+        if (wt == 128) trace(14);
         mbar_wait(&bar->dfull[2], 0);
         tc_fence_after();
+        if (wt == 0) trace(15);
         for (int cc = 0; cc < 2; ++cc) {
             const int c0 = hf * 64 + cc * 32;
             float r[32];
@@ -597,8 +675,10 @@ __global__ void __launch_bounds__(THREADS, 1) enc_ffn_kernel(const __grid_consta
             warp_store_block(stage, v, lane, a.x2 + grow0 * DM + c0, DM, nrows);
         }
         tc_fence_before();
+        if (wt == 0) trace(16);
     }
     tmem_free_512(tmem, warp);
+    if (threadIdx.x == 0) trace(17);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -676,6 +756,10 @@ static void set_smem(K kernel, int bytes) {
 
 using namespace gb200;
 using namespace gb200::enc;
+
+extern "C" int gb200_encoder_set_trace(unsigned long long* device_buffer) {
+    return cudaMemcpyToSymbol(g_enc_trace, &device_buffer, sizeof(device_buffer)) == cudaSuccess ? GB200_OK : GB200_ERR_CUDA;
+}
 
 extern "C" int gb200_encoder_supported(int d_model, int n_head, int pos_dim, int d_ff) {
     return d_model == DM && n_head == NH && d_ff == DFF && pos_dim >= 1 && pos_dim <= 2 && encode_fn() != nullptr;

@@ -38,10 +38,16 @@ def set_precision(mode):
     global _PRECISION
     assert mode in ("x3", "tf32", "fp32")
     _PRECISION = mode
+    # the stock cuDNN 3x3 convolutions of the interpolation scalers (out of scope) follow the mode:
+    # TF32 only in 'tf32' mode (torch's default would be TF32 always)
+    torch.backends.cudnn.allow_tf32 = mode == "tf32"
 
 
 def get_precision():
     return _PRECISION
+
+
+torch.backends.cudnn.allow_tf32 = _PRECISION == "tf32"
 
 _seed_lock = threading.Lock()
 _seed_counter = 0

@@ -276,6 +276,9 @@ typedef struct gb200_encoder_params {
     int d_model, n_head, pos_dim, d_ff;
 } gb200_encoder_params;
 int gb200_encoder_supported(int d_model, int n_head, int pos_dim, int d_ff);
+/* Diagnostics: non-null = every CTA of the fused encoder kernels writes clock64 stamps of its pipeline milestones to
+ * device_buffer[32 * blockIdx.x + slot] (slot 31: %globaltimer at entry); tools/trace_fused.py prints the timeline. */
+int gb200_encoder_set_trace(unsigned long long* device_buffer);
 size_t gb200_encoder_pack_bytes(int d_model, int n_head, int pos_dim, int d_ff);
 int gb200_encoder_pack(int device, const gb200_encoder_params* params, void* packed, void* stream);
 size_t gb200_encoder_workspace_bytes(int B, int n, int n_head, int d_k, int pos_dim);

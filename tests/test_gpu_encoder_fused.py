@@ -1,0 +1,125 @@
+"""GPU parity of the fused encoder-layer kernels (csrc/encoder_fwd.cu, encoder_bwd.cu; 'x3' precision mode).
+
+  * every kernel alone, fed reference inputs, against a torch fp64 restatement of libs/model.py:104-140 /
+    libs/layers.py:829-899, 979-987 (tools/debug_fused.py holds the restatement), ragged and aligned token counts,
+    pos_dim 1 and 2;
+  * the module path: fused layer == per-operator exact-fp32 layer, outputs and every gradient, with ALL dropouts
+    active and identical seeds (the fused epilogues draw the same Philox streams as the unfused ones);
+  * the oracle at C3 size.
+Tolerances (relative L2, bf16x3 arithmetic ~2^-17 per product): forward 5e-5, gradients 1e-3."""
+import os
+import sys
+
+import pytest
+import torch
+
+import galerkin_transformer_b200 as G
+from galerkin_transformer_b200 import functional as GF
+from helpers import rel_l2
+from oracle import galerkin_oracle as O
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import debug_fused as DF          # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+FWD_TOL, GRAD_TOL = 5e-5, 1e-3
+
+
+@pytest.fixture(autouse=True)
+def _x3():
+    G.set_precision("x3")
+    yield
+    G.set_precision("x3")
+
+
+@pytest.mark.parametrize("B,n,p", [(2, 300, 2), (1, 128, 2), (3, 129, 1), (2, 1849, 2), (1, 57, 2)])
+def test_fused_forward_kernels_against_fp64(B, n, p):
+    eps = 1e-6
+    P, x, pos, keep = DF.make(B, n, p, seed=B * 1000 + n)
+    R = DF.reference(P, x, pos, keep, eps)
+    packed = DF.do_pack(P, p)
+    assert DF.check_pack(P, p, packed)
+    o = DF.run_stage(1, P, x, pos, keep, packed, R, eps)
+    assert rel_l2(o["qkv"], R["qkv"]) < FWD_TOL
+    assert rel_l2(o["rk"], R["rk"]) < FWD_TOL and rel_l2(o["rv"], R["rv"]) < FWD_TOL
+    assert rel_l2(o["ws"].sum(1), R["Araw"]) < FWD_TOL
+    o = DF.run_stage(2, P, x, pos, keep, packed, R, eps)
+    for k in ("A", "heads", "x1"):
+        assert rel_l2(o[k], R[k]) < FWD_TOL, k
+    o = DF.run_stage(4, P, x, pos, keep, packed, R, eps)
+    for k in ("hid", "x2"):
+        assert rel_l2(o[k], R[k]) < FWD_TOL, k
+    o = DF.run_stage(7, P, x, pos, keep, packed, R, eps)
+    for k in ("qkv", "A", "heads", "x1", "hid", "x2"):
+        assert rel_l2(o[k], R[k]) < FWD_TOL, k
+
+
+def _layer(dropout, seed=0, residual_type="add"):
+    torch.manual_seed(seed)
+    m = G.SimpleTransformerEncoderLayer(d_model=128, n_head=4, pos_dim=2, dim_feedforward=256, attention_type="galerkin",
+                                        layer_norm=False, attn_norm=True, norm_eps=1e-7, dropout=dropout,
+                                        ffn_dropout=dropout, residual_type=residual_type)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for prm in m.parameters():
+            prm.add_((0.2 if prm.ndim == 1 else 0.02) * torch.randn(prm.shape, generator=g))
+    return m.to(DEV)
+
+
+def _run(m, x, pos, cot, mode, attn_dropout):
+    G.set_precision(mode)
+    G.set_attn_dropout(m, attn_dropout)
+    GF._seed_counter = 0            # identical Philox keys for both paths
+    xx = x.detach().clone().requires_grad_(True)
+    y = m(xx, pos)
+    grads = torch.autograd.grad((y * cot).sum(), [xx] + list(m.parameters()))
+    return y.detach(), [g.detach() for g in grads], m.attn.attn_weight.detach()
+
+
+@pytest.mark.parametrize("B,n,dropout,attn_dropout,residual_type", [
+    (2, 300, 0.0, "off", "add"), (2, 300, 0.1, "reference", "add"), (8, 1849, 0.05, "reference", "add"),
+    (1, 200, 0.1, "reference", "minus")])
+def test_fused_layer_equals_unfused_fp32_layer(B, n, dropout, attn_dropout, residual_type):
+    """same module, same seeds: fused 'x3' path vs exact-fp32 per-operator path"""
+    m = _layer(dropout, residual_type=residual_type)
+    m.train()
+    g = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.randn(B, n, 128, device=DEV, generator=g)
+    pos = torch.rand(B, n, 2, device=DEV, generator=g)
+    cot = torch.randn(B, n, 128, device=DEV, generator=g)
+    y0, g0, A0 = _run(m, x, pos, cot, "fp32", attn_dropout)
+    assert not m._fused_ok(x, pos, None)
+    G.set_precision("x3")
+    assert m._fused_ok(x, pos, None), "fused path not taken"
+    y1, g1, A1 = _run(m, x, pos, cot, "x3", attn_dropout)
+    assert rel_l2(y1, y0) < FWD_TOL
+    assert rel_l2(A1, A0) < FWD_TOL
+    if attn_dropout == "reference":
+        assert torch.equal(A1 == 0, A0 == 0)              # identical attention-dropout mask
+    names = ["x"] + [k for k, _ in m.named_parameters()]
+    for k, a, b in zip(names, g1, g0):
+        assert rel_l2(a, b) < GRAD_TOL, (k, rel_l2(a, b))
+
+
+def test_fused_layer_matches_oracle_at_c3_size():
+    m = _layer(0.0, seed=5)
+    G.set_attn_dropout(m, "off")
+    B, n = 8, 1849
+    g = torch.Generator(device=DEV).manual_seed(4)
+    x = torch.randn(B, n, 128, device=DEV, generator=g, requires_grad=True)
+    gr = torch.linspace(0, 1, 43, device=DEV)
+    pos = torch.stack(torch.meshgrid(gr, gr, indexing="ij"), -1).reshape(1, n, 2).repeat(B, 1, 1)
+    assert m._fused_ok(x, pos, None)
+    y = m(x, pos)
+    cot = torch.randn(B, n, 128, device=DEV, generator=g)
+    params = dict(m.named_parameters())
+    grads = torch.autograd.grad((y * cot).sum(), [x] + list(params.values()))
+    sd = {k: v.detach().double().requires_grad_(True) for k, v in m.state_dict().items()}
+    xd = x.detach().double().requires_grad_(True)
+    yr = O.encoder_layer(sd, "", xd, pos.double(), n_head=4, attention_type="galerkin", layer_norm=False, attn_norm=True,
+                         norm_eps=1e-7, pos_dim=2)
+    gref = torch.autograd.grad((yr * cot.double()).sum(), [xd] + [sd[k] for k in params])
+    assert rel_l2(y, yr) < FWD_TOL
+    for k, a, b in zip(["x"] + list(params), grads, gref):
+        assert rel_l2(a, b) < GRAD_TOL, (k, rel_l2(a, b))

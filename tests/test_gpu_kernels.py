@@ -19,7 +19,7 @@ def _exact_fp32_by_default():
     """Kernel tests check the exact-fp32 path unless they opt into the tensor-core path."""
     GF.set_precision("fp32")
     yield
-    GF.set_precision("tf32")
+    GF.set_precision("x3")
 
 
 def rn(*s, seed=0):

@@ -19,14 +19,18 @@ DEV = "cuda"
 # TF32 gradients through a ReLU FFN carry sign-flip noise ~ sqrt(P(|z| < eps_tf32)) ~ 2e-2 that any
 # reduced-precision implementation has (see test_gpu_kernels.py::test_linear_autograd_tensor_cores), hence
 # grad = 3e-2 for the ReLU encoder graphs; smooth graphs are held to 5e-3 there.
-TOLS = {"fp32": dict(fwd=1e-5, grad=1e-4, model=1e-3), "tf32": dict(fwd=2e-3, grad=3e-2, model=3e-2)}
+# "x3" (the default and the benchmarked mode: bf16x3 fused encoder kernels, TF32 weight gradients, exact fp32 elsewhere)
+# is held to ABSOLUTE tolerances, tighter than SURVEY 8c's TF32 column: forward 5e-5, gradients 1e-3, 10-layer model
+# loss 1e-3 / input gradient 1e-2.
+TOLS = {"fp32": dict(fwd=1e-5, grad=1e-4, model=1e-3), "x3": dict(fwd=5e-5, grad=1e-3, model=1e-2),
+        "tf32": dict(fwd=2e-3, grad=3e-2, model=3e-2)}
 
 
-@pytest.fixture(params=["fp32", "tf32"], autouse=True)
+@pytest.fixture(params=["fp32", "x3", "tf32"], autouse=True)
 def precision(request):
     G.set_precision(request.param)
     yield request.param
-    G.set_precision("tf32")
+    G.set_precision("x3")
 # the stock cuDNN convolutions of the (out-of-scope) scalers default to TF32; parity is fp32
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
@@ -188,7 +192,7 @@ def test_encoder_layer_matches_oracle_at_baseline_sizes(cfg, B, n, precision):
         # fp32 mode: measured at C4 size, |d beta_Q[3]| = 23 is what is left of sums whose terms add up to ~2 000
         # (and |d W_lr1| = 13 800): 2.1e-4 / 1.5e-4 relative, i.e. ~2e-6 of the summed magnitudes; cuBLAS/ATen fp32
         # reach 6e-6 on the same quantity with their pairwise accumulation orders.  Accepted up to 1e-3 HERE ONLY.
-        floor = 1e-3 if precision == "fp32" else 0.0
+        floor = 1e-3 if precision in ("fp32", "x3") else 0.0
         assert err < max(3.0 * ref32 + 1e-6, floor), (k, err, "eager PyTorch itself:", ref32)
 
 
@@ -270,6 +274,13 @@ def test_full_model_c3_matches_oracle(precision):
         assert mine[0] < max(1e-3, 3 * loss_yard), (mine, loss_yard)
         assert mine[1] < max(3e-2, 3 * grad_yard), (mine, grad_yard)
         return
+    print(f"C3 {precision}: loss rel {abs(loss.item() - ref.item()) / abs(ref.item()):.2e}; dnode rel "
+          f"{rel_l2(gnode, gref):.2e} (eager-fp32 {eager_err:.2e})")
+    if precision == "x3":
+        # the benchmarked mode, absolute SURVEY 8c bars: model loss 1e-3, 10-layer end-to-end gradient 1e-2
+        assert abs(loss.item() - ref.item()) / abs(ref.item()) < 1e-3
+        assert rel_l2(gnode, gref) < 1e-2
+        return
     assert abs(loss.item() - ref.item()) / abs(ref.item()) < 1e-4
     # stated tolerance for the 10-layer end-to-end gradient: 1e-2, and never worse than 3x what
     # fp32 eager PyTorch itself achieves on the same graph
@@ -308,7 +319,7 @@ def test_graphed_step_matches_eager_and_refreshes_dropout(precision):
         for g, p_ in zip(grads, model.parameters()):
             # our kernels are run-to-run deterministic, but cuDNN may pick other conv algorithms under capture;
             # in TF32 mode that upstream round-off is amplified like any other perturbation
-            assert rel_l2(g, p_.grad) < (1e-4 if G.get_precision() == "fp32" else 2e-2)
+            assert rel_l2(g, p_.grad) < (1e-4 if G.get_precision() == "fp32" else (1e-3 if G.get_precision() == "x3" else 2e-2))
     # dropout on: replays must differ from each other
     cfg2 = c3_config()
     cfg2["num_encoder_layers"] = 2
@@ -348,7 +359,7 @@ def test_micro_batch_chains_give_the_full_batch_gradient(chains, precision):
     for lv, grads in outs:
         assert abs(lv - full.item()) < 1e-5 * abs(full.item()) + 1e-9
         for g, p_ in zip(grads, model.parameters()):
-            assert rel_l2(g, p_.grad) < (1e-4 if G.get_precision() == "fp32" else 2e-2), rel_l2(g, p_.grad)
+            assert rel_l2(g, p_.grad) < (1e-4 if G.get_precision() == "fp32" else (1e-3 if G.get_precision() == "x3" else 2e-2)), rel_l2(g, p_.grad)
 
 
 @pytest.mark.parametrize("B,H,n,dk,p", [(2, 4, 200, 48, 2), (1, 2, 333, 16, 1), (2, 1, 130, 62, 2)])
