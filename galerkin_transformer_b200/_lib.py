@@ -111,6 +111,12 @@ SIGNATURES = {
     "gb200_encoder_layer_fwd": (c_int, [c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_int, c_int, c_float,
                                         c_float, c_vp, c_float, c_ull, c_float, c_ull, c_float, c_float, c_ull, c_float,
                                         c_ull, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_int, c_vp]),
+    "gb200_encoder_bwd_workspace_bytes": (c_sz, [c_int] * 5),
+    "gb200_encoder_bwd_set_trace": (c_int, [c_vp]),
+    "gb200_encoder_layer_bwd": (c_int, [c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_int, c_int, c_float,
+                                        c_vp, c_float, c_ull, c_float, c_ull, c_float, c_float, c_float, c_ull,
+                                        c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz,
+                                        c_int, c_vp]),
 }
 
 

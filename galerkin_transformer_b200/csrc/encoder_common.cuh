@@ -285,5 +285,32 @@ __device__ __forceinline__ void tmem_free_512(uint32_t base, int warp) {
     }
 }
 
+// ---- layer geometry (BASELINE config 3) and the packed-parameter layout shared by forward and backward ----------
+constexpr int DM = 128, NH = 4, DK = 32, DFF = 256, HP = 48;     // HP: padded head width of the fc operand (>= DK + 2)
+constexpr int VEC_BQKV = 0, VEC_GK = 384, VEC_BK = 512, VEC_GV = 640, VEC_BV = 768, VEC_BFC = 896, VEC_B1 = 1024,
+              VEC_B2 = 1280, VEC_FLOATS = 1408;
+// forward tile stream (tiles of TILE_BYTES): W_qkv 12 | W_fc' 6 | W1 8 | W2 8
+constexpr int TS_QKV = 0, TS_FC = 12, TS_W1 = 18, TS_W2 = 26;
+// backward stream: W2^T 8 | W1^T 8 | W_fc'^T 8 | W_qkv^T 12
+constexpr int TS_W2T = 34, TS_W1T = 42, TS_FCT = 50, TS_QKVT = 58;
+
+struct Bars {
+    uint64_t xfull, xconv, full[6], empty[6], dfull[4], hand[4], done;
+    uint32_t tmem_slot;
+};
+
+static inline bool make_tile_map(CUtensorMap* m, const float* base, int ld, int n, int B) {
+    cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)n, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)ld * 4 * (cuuint64_t)n};
+    cuuint32_t box[3] = {32, (cuuint32_t)TM, 1};
+    return make_map_nd(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+template <typename K>
+static inline void set_smem(K kernel, int bytes) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+
 }  // namespace enc
 }  // namespace gb200

@@ -290,6 +290,26 @@ int gb200_encoder_layer_fwd(int device, const void* packed, int d_model, int n_h
                             float* rstd_k, float* rstd_v, float* attn, float* heads, float* x1, float* hidden, float* x2,
                             float* workspace, size_t workspace_bytes, int stages, void* stream);
 
+/* Backward of the fused layer (csrc/encoder_bwd.cu): four tcgen05 kernels + one reduction carry every input-gradient
+ * GEMM (bf16x3), the activation / dropout / per-head LayerNorm backward passes and all bias / LayerNorm-parameter
+ * gradients; the caller runs the four weight-gradient GEMMs (dW2 = g2^T hidden, dW1 = g1^T x1, dW_fc = gfc^T heads,
+ * dW_qkv = dqkv^T x) on gb200_gemm_tc from the buffers written here.
+ *   g2 (B n, d_model) = dy * mask_out      (written only when p_out > 0; otherwise dy itself)
+ *   g1 (B n, d_ff), dx1 (B n, d_model), gfc (B n, d_model) = sign * dx1 * mask_attn_out (only when it differs from dx1),
+ *   dqkv (B n, 3 d_model), dx (B n, d_model), dvec (1408 floats, the layout of the packed vector block:
+ *   d b_q | d b_k | d b_v | d gamma_K | d beta_K | d gamma_V | d beta_V | d b_fc | d b_1 | d b_2).
+ * `stages`: bit 0 ffn, 1 attention-out, 2 K/V + LayerNorm, 3 dx, 4 reduction (31 = everything). */
+size_t gb200_encoder_bwd_workspace_bytes(int B, int n, int n_head, int d_k, int pos_dim);
+int gb200_encoder_bwd_set_trace(unsigned long long* device_buffer);
+int gb200_encoder_layer_bwd(int device, const void* packed, int d_model, int n_head, int pos_dim, int d_ff,
+                            const float* dy, const float* pos, int B, int n, int has_norm, float attn_scale,
+                            const unsigned char* keep_mask, float mask_p, unsigned long long mask_seed, float p_attn_out,
+                            unsigned long long seed_attn_out, float res_sign, float p_ffn, float p_out,
+                            unsigned long long seed_out, const float* qkv, const float* rstd_k, const float* rstd_v,
+                            const float* attn, const float* hidden, float* g2, float* g1, float* dx1, float* gfc,
+                            float* dqkv, float* dx, float* dvec, float* workspace, size_t workspace_bytes, int stages,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,6 +73,142 @@ def reference(P, x, pos, keep, eps, sign=1.0):
     return dict(qkv=torch.cat([q, kh, vh], 1), rk=rk, rv=rv, Araw=Araw, A=A, heads=heads, x1=x1, hid=hid, x2=x2)
 
 
+def reference_backward(P, x, pos, keep, eps, dy, sign=1.0):
+    """fp64 backward of `reference` for the cotangent dy (B n, 128): every buffer the fused backward kernels write.
+    Parameter gradients come from autograd on the same fp64 graph."""
+    D = lambda t: t.double()
+    B, n, _ = x.shape
+    p = pos.shape[-1]
+    d = DK + p
+    leaves = {k: (D(v).clone().requires_grad_(True) if torch.is_tensor(v) else [D(t).clone().requires_grad_(True) for t in v])
+              for k, v in P.items()}
+    X = D(x).reshape(B * n, DM).clone().requires_grad_(True)
+    q = X @ leaves["wq"].t() + leaves["bq"]
+    k = X @ leaves["wk"].t() + leaves["bk"]
+    v = X @ leaves["wv"].t() + leaves["bv"]
+    for t in (q, k, v):
+        t.retain_grad()
+
+    def hn(t, gam, bet):
+        t = t.view(B * n, H, DK)
+        mu = t.mean(-1, keepdim=True)
+        var = ((t - mu) ** 2).mean(-1, keepdim=True)
+        xh = (t - mu) / torch.sqrt(var + eps)
+        return xh * torch.stack(gam)[None] + torch.stack(bet)[None]
+
+    ka, va = hn(k, leaves["gk"], leaves["bek"]), hn(v, leaves["gv"], leaves["bev"])
+    pp = D(pos).reshape(B, n, 1, p).expand(B, n, H, p)
+    Kt = torch.cat([pp, ka.view(B, n, H, DK)], -1).permute(0, 2, 1, 3)
+    Vt = torch.cat([pp, va.view(B, n, H, DK)], -1).permute(0, 2, 1, 3)
+    Qt = torch.cat([pp, q.view(B, n, H, DK)], -1).permute(0, 2, 1, 3)
+    A = (Kt.transpose(-1, -2) @ Vt) / n * (2.0 * D(keep))
+    heads = (Qt @ A).permute(0, 2, 1, 3).reshape(B * n, H * d)
+    heads.retain_grad()
+    x1 = X + sign * (heads @ leaves["wfc"].t() + leaves["bfc"])
+    x1.retain_grad()
+    z1 = x1 @ leaves["w1"].t() + leaves["b1"]
+    z1.retain_grad()
+    x2 = x1 + torch.relu(z1) @ leaves["w2"].t() + leaves["b2"]
+    flat = [leaves[k_] for k_ in ("wq", "wk", "wv", "bq", "bk", "bv")] + leaves["gk"] + leaves["bek"] + leaves["gv"] + \
+        leaves["bev"] + [leaves[k_] for k_ in ("wfc", "bfc", "w1", "b1", "w2", "b2")]
+    grads = torch.autograd.grad((x2 * D(dy).reshape(B * n, DM)).sum(), [X] + flat, retain_graph=False)
+    dO = heads.grad.view(B, n, H, d).permute(0, 2, 1, 3)                       # B,H,n,d
+    Graw = Qt.detach().transpose(-1, -2) @ dO                                  # B,H,d,d (unscaled, unmasked)
+    o = 7 + 4 * H
+    dvec = torch.cat([grads[4], grads[5], grads[6], *grads[7:o], grads[o + 1], grads[o + 3], grads[o + 5]])
+    return dict(g1=z1.grad, dx1=x1.grad, dheads=heads.grad, dqkv=torch.cat([q.grad, k.grad, v.grad], 1), dx=grads[0],
+                Graw=Graw, dvec=dvec, dwq=grads[1], dwk=grads[2], dwv=grads[3], dwfc=grads[o], dw1=grads[o + 2],
+                dw2=grads[o + 4])
+
+
+def run_bwd_stage(stage, P, x, pos, keep, packed, R, RB, dy, eps):
+    """stage bit (1 ffn, 2 attn-out, 4 kv, 8 dx, 16 reduce) fed with reference inputs; 31 = everything chained"""
+    lib = _lib.load()
+    B, n, _ = x.shape
+    p = pos.shape[-1]
+    d = DK + p
+    T = B * n
+    tiles = (n + 127) // 128
+    f32 = dict(dtype=torch.float32, device="cuda")
+    chain = stage == 31
+    qkv = R["qkv"].float().contiguous()
+    rk, rv = R["rk"].float().contiguous(), R["rv"].float().contiguous()
+    A = R["A"].float().contiguous()
+    hid = R["hid"].float().contiguous()
+    g2 = torch.zeros(T, DM, **f32)
+    g1 = torch.zeros(T, DFF, **f32)
+    dx1 = torch.zeros(T, DM, **f32) if (chain or stage == 1) else RB["dx1"].float().contiguous()
+    gfc = torch.zeros(T, DM, **f32)
+    dqkv = torch.zeros(T, 3 * DM, **f32) if (chain or stage in (2, 4)) else RB["dqkv"].float().contiguous()
+    dx = torch.zeros(T, DM, **f32)
+    dvec = torch.zeros(1408, **f32)
+    nws = lib.gb200_encoder_bwd_workspace_bytes(B, n, H, DK, p) // 4
+    ws = torch.zeros(nws, **f32)
+    if stage == 4:
+        ws[:B * tiles * H * d * d].view(B, tiles, H, d, d)[:, 0] = RB["Graw"].float()
+    dyc = dy.reshape(T, DM).contiguous()
+    rc = lib.gb200_encoder_layer_bwd(0, packed.data_ptr(), DM, H, p, DFF, dyc.data_ptr(), pos.data_ptr(), B, n, 1, 1.0 / n,
+                                     keep.data_ptr(), 0.0, 0, 0.0, 11, 1.0, 0.0, 0.0, 33, qkv.data_ptr(), rk.data_ptr(),
+                                     rv.data_ptr(), A.data_ptr(), hid.data_ptr(), g2.data_ptr(), g1.data_ptr(),
+                                     dx1.data_ptr(), gfc.data_ptr(), dqkv.data_ptr(), dx.data_ptr(), dvec.data_ptr(),
+                                     ws.data_ptr(), ws.numel() * 4, stage, torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "encoder_layer_bwd")
+    torch.cuda.synchronize()
+    gp = ws[:B * tiles * H * d * d].view(B, tiles, H, d, d)
+    part = ws[B * tiles * H * d * d:].view(B * tiles, 1408)
+    return dict(g1=g1, dx1=dx1, dqkv=dqkv, dx=dx, dvec=dvec, gpart=gp, part=part)
+
+
+def check_backward(P, x, pos, keep, packed, R, eps, stages=("1", "2", "4", "8", "31"), tol=1e-4):
+    g = torch.Generator(device="cuda").manual_seed(77)
+    dy = torch.randn(x.shape, device="cuda", generator=g)
+    RB = reference_backward(P, x, pos, keep, eps, dy)
+    ok = True
+    V = dict(bqkv=(0, 384), gk=(384, 512), bk=(512, 640), gv=(640, 768), bv=(768, 896), bfc=(896, 1024), b1=(1024, 1280),
+             b2=(1280, 1408))
+
+    def seg(t, name):
+        return t[..., V[name][0]:V[name][1]]
+    if "1" in stages:
+        o = run_bwd_stage(1, P, x, pos, keep, packed, R, RB, dy, eps)
+        e = dict(g1=rel(o["g1"], RB["g1"]), dx1=rel(o["dx1"], RB["dx1"]), db1=rel(seg(o["part"].sum(0), "b1"), seg(RB["dvec"], "b1")),
+                 db2=rel(seg(o["part"].sum(0), "b2"), seg(RB["dvec"], "b2")))
+        print("bwd 1 (ffn)   :", {k: f"{v:.2e}" for k, v in e.items()})
+        ok &= max(e.values()) < tol
+    if "2" in stages:
+        o = run_bwd_stage(2, P, x, pos, keep, packed, R, RB, dy, eps)
+        e = dict(dq=rel(o["dqkv"][:, :128], RB["dqkv"][:, :128]), G=rel(o["gpart"].sum(1), RB["Graw"]),
+                 dbfc=rel(seg(o["part"].sum(0), "bfc"), seg(RB["dvec"], "bfc")))
+        p = pos.shape[-1]
+        Go, Gr = o["gpart"].sum(1).double(), RB["Graw"]
+        e["G_ff"] = rel(Go[..., p:, p:], Gr[..., p:, p:])
+        e["G_fp"] = rel(Go[..., p:, :p], Gr[..., p:, :p])
+        e["G_pf"] = rel(Go[..., :p, p:], Gr[..., :p, p:])
+        e["G_pp"] = rel(Go[..., :p, :p], Gr[..., :p, :p])
+        print("bwd 2 (attn)  :", {k: f"{v:.2e}" for k, v in e.items()})
+        ok &= max(e.values()) < tol
+    if "4" in stages:
+        o = run_bwd_stage(4, P, x, pos, keep, packed, R, RB, dy, eps)
+        e = dict(dk=rel(o["dqkv"][:, 128:256], RB["dqkv"][:, 128:256]), dv=rel(o["dqkv"][:, 256:], RB["dqkv"][:, 256:]))
+        for nm in ("gk", "bk", "gv", "bv"):
+            e["d" + nm] = rel(seg(o["part"].sum(0), nm), seg(RB["dvec"], nm))
+        print("bwd 3 (kv+LN) :", {k: f"{v:.2e}" for k, v in e.items()})
+        ok &= max(e.values()) < tol
+    if "8" in stages:
+        o = run_bwd_stage(8, P, x, pos, keep, packed, R, RB, dy, eps)
+        e = dict(dx=rel(o["dx"], RB["dx"]), dbqkv=rel(seg(o["part"].sum(0), "bqkv"), seg(RB["dvec"], "bqkv")))
+        print("bwd 4 (dx)    :", {k: f"{v:.2e}" for k, v in e.items()})
+        ok &= max(e.values()) < tol
+    if "31" in stages:
+        o = run_bwd_stage(31, P, x, pos, keep, packed, R, RB, dy, eps)
+        e = dict(g1=rel(o["g1"], RB["g1"]), dx1=rel(o["dx1"], RB["dx1"]), dqkv=rel(o["dqkv"], RB["dqkv"]), dx=rel(o["dx"], RB["dx"]))
+        for nm in V:
+            e["d" + nm] = rel(seg(o["dvec"], nm), seg(RB["dvec"], nm))
+        print("bwd all       :", {k: f"{v:.2e}" for k, v in e.items()})
+        ok &= max(e.values()) < tol
+    return ok
+
+
 def unswizzle(tile_u8):
     """16 KB tile image -> (128, 64) bf16 tensor"""
     t = tile_u8.view(torch.int16).view(128, 8, 8)              # row, physical unit, 8 elems
@@ -221,6 +357,9 @@ def main():
         e = {k: rel(o[k], R[k]) for k in ("qkv", "rk", "rv", "A", "heads", "x1", "hid", "x2")}
         print("layer  :", {k: f"{v:.2e}" for k, v in e.items()})
         ok &= max(e.values()) < 1e-4
+    if args.stage.startswith("b"):
+        sel = ("1", "2", "4", "8", "31") if args.stage == "b" else (args.stage[1:],)
+        ok &= check_backward(P, x, pos, keep, packed, R, eps, sel)
     print("OK" if ok else "FAILED")
     return 0 if ok else 1
 
