@@ -167,6 +167,48 @@ class _Fork:
             self.main.wait_stream(s)
         self.used = []
 
+    def join_at_end_of_backward(self, keepalive):
+        """Do not wait now: the launching stream joins the side streams when the whole backward pass has been enqueued
+        (autograd engine callback), so weight-gradient GEMMs of layer l overlap the input-gradient chain of layers
+        l-1, l-2, ...  `keepalive`: every tensor the side work reads or writes -- held until the join so the caching
+        allocator cannot hand their memory to later launches of the same pass."""
+        global _join_queued
+        if not self.used:
+            return
+        with _seed_lock:
+            _pending_joins.append((self.main, list(self.used), keepalive))
+            queue = not _join_queued
+            _join_queued = True
+        self.used = []
+        if queue:
+            torch.autograd.Variable._execution_engine.queue_callback(_join_pending)
+
+
+_aux_streams = {}
+
+
+def aux_stream(device):
+    """one auxiliary stream per device for work that is independent of the critical path (parameter packing)"""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _aux_streams:
+        _aux_streams[key] = torch.cuda.Stream(device=device)
+    return _aux_streams[key]
+
+
+_pending_joins = []
+_join_queued = False
+
+
+def _join_pending():
+    global _join_queued
+    with _seed_lock:
+        items = list(_pending_joins)
+        _pending_joins.clear()
+        _join_queued = False
+    for main, streams, _keep in items:
+        for st in streams:
+            main.wait_stream(st)
+
 
 # ------------------------------------------------------------------------------------------
 # raw launches
@@ -794,11 +836,28 @@ def linear_attention(query, key, value, pos, flat, has_norm, keep_mask, *, n_hea
 # ------------------------------------------------------------------------------------------
 # Fused encoder layer (csrc/encoder_fwd.cu): three tcgen05 kernels per layer forward
 # ------------------------------------------------------------------------------------------
+_FUSED_BACKWARD = os.environ.get("GB200_FUSED_BACKWARD", "1") != "0"     # A/B switch: 0 = per-operator backward
+# 1 = the launching stream joins the weight-gradient side streams only when the whole backward pass is enqueued.  Measured
+# at C3: 7.28 vs 7.33 ms/step -- the GEMMs are not dependency- but SM-bound (a fused-kernel CTA owns its SM's shared
+# memory), and the late join is unsafe with concurrent micro-batch chains, so it stays opt-in.
+_DEFER_WGRAD_JOIN = os.environ.get("GB200_DEFER_WGRAD_JOIN", "0") == "1"
+
+
 class _Ctx:
     """stand-in autograd context for calling another Function's backward on explicit tensors"""
 
     def __init__(self, saved, cfg, needs):
         self.saved_tensors, self.cfg, self.needs_input_grad = saved, cfg, needs
+
+
+def encoder_pack(params, H, dm, p, dff):
+    """parameters -> bf16 (hi, lo) operand tile streams + fp32 vector block of the fused kernels (one launch)"""
+    lib = _lib.load()
+    P, _ = _encoder_params_struct(params, H, dm, p, dff)
+    packed = torch.empty(lib.gb200_encoder_pack_bytes(dm, H, p, dff), dtype=torch.uint8, device=params[0].device)
+    _launch("encoder_pack", 0.0, 2.0 * packed.numel(), lib.gb200_encoder_pack, _dev(packed), ctypes.byref(P), ptr(packed),
+            stream_of(packed))
+    return packed
 
 
 def encoder_fused_supported(d_model, n_head, pos_dim, d_ff):
@@ -829,7 +888,7 @@ class _EncoderLayerFn(torch.autograd.Function):
               streams), see _LinearAttentionFn / _LinearFn / _MLP2Fn."""
 
     @staticmethod
-    def forward(ctx, x, pos, keep_mask, cfg, *params):
+    def forward(ctx, x, pos, keep_mask, cfg, packed, *params):
         (H, p, eps, scale, mask_p, mask_seed, p1, seed1, sign, pf, seedf, p2, seed2) = cfg
         require_cuda_f32(x, pos, *params)
         lib = _lib.load()
@@ -838,9 +897,9 @@ class _EncoderLayerFn(torch.autograd.Function):
         dff = params[-4].shape[0]
         T = B * n
         dev, st = _dev(x), stream_of(x)
-        P, has_norm = _encoder_params_struct(params, H, dm, p, dff)
-        packed = torch.empty(lib.gb200_encoder_pack_bytes(dm, H, p, dff), dtype=torch.uint8, device=x.device)
-        _launch("encoder_pack", 0.0, 2.0 * packed.numel(), lib.gb200_encoder_pack, dev, ctypes.byref(P), ptr(packed), st)
+        has_norm = len(params) == 4 * H + 12
+        if packed is None:
+            packed = encoder_pack(params, H, dm, p, dff)
         f32 = dict(dtype=torch.float32, device=x.device)
         qkv = torch.empty((T, 3 * dm), **f32)
         rstd = [torch.empty((T, H), **f32) for _ in range(2)] if has_norm else [None, None]
@@ -878,6 +937,8 @@ class _EncoderLayerFn(torch.autograd.Function):
         if dy is None:
             dy = torch.zeros_like(x)
         dy2 = dy.reshape(T, dm).contiguous()
+        if dA_ext is None and _FUSED_BACKWARD:
+            return _EncoderLayerFn._backward_fused(ctx, dy2, x, pos, keep_mask, qkv, A, heads, x1, hid, packed, rstd, params)
         # FeedForward + shortcut
         c = _Ctx((x1, w1, w2, hid, None), (ACT["relu"], pf, seedf, p2, seed2, 1.0, True, True, True), (True,) * 12)
         dx1, dw1, db1, dw2, db2 = _MLP2Fn.backward(c, dy2)[:5]
@@ -899,18 +960,78 @@ class _EncoderLayerFn(torch.autograd.Function):
         if has_norm:
             grads += [dflat[o + i * dk:o + (i + 1) * dk] for i in range(4 * H)]
         grads += [dwfc, dbfc, dw1, db1, dw2, db2]
-        return (dx, None, None, None, *grads)
+        return (dx, None, None, None, None, *grads)
+
+
+    @staticmethod
+    def _backward_fused(ctx, dy2, x, pos, keep_mask, qkv, A, heads, x1, hid, packed, rstd, params):
+        """csrc/encoder_bwd.cu: four fused kernels on the launching stream; the four weight-gradient GEMMs (TF32 tcgen05,
+        contractions over all tokens) fork onto the side streams as soon as their operands exist."""
+        (H, p, eps, scale, mask_p, mask_seed, p1, seed1, sign, pf, seedf, p2, seed2) = ctx.cfg
+        lib = _lib.load()
+        B, n, dm = x.shape
+        dk, d = dm // H, dm // H + p
+        dff = hid.shape[1]
+        T = B * n
+        dev, st = _dev(x), stream_of(x)
+        has_norm = ctx.has_norm
+        f32 = dict(dtype=torch.float32, device=x.device)
+        g2 = torch.empty((T, dm), **f32) if p2 > 0.0 else None
+        need_gfc = p1 > 0.0 or sign != 1.0
+        gfc = torch.empty((T, dm), **f32) if need_gfc else None
+        g1 = torch.empty((T, dff), **f32)
+        dx1 = torch.empty((T, dm), **f32)
+        dqkv = torch.empty((T, 3 * dm), **f32)
+        dx = torch.empty((B, n, dm), **f32)
+        dvec = torch.empty(3 * dm + 4 * dm + dm + dff + dm, **f32)
+        dw2, dw1, dwfc = torch.empty_like(params[-2]), torch.empty_like(params[-4]), torch.empty_like(params[-6])
+        dwqkv = torch.empty((3 * dm, dm), **f32)
+        wsb = lib.gb200_encoder_bwd_workspace_bytes(B, n, H, dk, p)
+        ws = workspace(wsb, x)
+
+        def stage(bits, flops, nbytes):
+            _launch("encoder_layer_bwd", flops, nbytes, lib.gb200_encoder_layer_bwd, dev, ptr(packed), dm, H, p, dff, ptr(dy2),
+                    ptr(pos), B, n, int(has_norm), scale, ptr(keep_mask), mask_p, mask_seed, p1, seed1, sign, pf, p2, seed2,
+                    ptr(qkv), ptr(rstd[0]) if has_norm else None, ptr(rstd[1]) if has_norm else None, ptr(A), ptr(hid),
+                    ptr(g2), ptr(g1), ptr(dx1), ptr(gfc), ptr(dqkv), ptr(dx), ptr(dvec), ptr(ws), wsb, bits, st)
+
+        fork = _Fork(dy2)
+        stage(1, 4.0 * T * dm * dff, 4.0 * T * (3 * dm + 2 * dff))
+        with fork.side(0):
+            gemm(g2 if g2 is not None else dy2, hid, dw2, dm, dff, T, lda=dm, ldb=dff, ldc=dff, transA=True, wgrad=True)
+        with fork.side(1):
+            gemm(g1, x1, dw1, dff, dm, T, lda=dff, ldb=dm, ldc=dm, transA=True, wgrad=True)
+        stage(2, 2.0 * T * H * d * dm + 8.0 * B * H * n * d * d, 4.0 * T * (4 * dm))
+        with fork.side(2):
+            gemm(gfc if gfc is not None else dx1, heads.reshape(T, H * d), dwfc, dm, H * d, T, lda=dm, ldb=H * d, ldc=H * d,
+                 transA=True, wgrad=True)
+        stage(4, 8.0 * B * H * n * d * d, 4.0 * T * (4 * dm))
+        stage(8, 2.0 * T * 3 * dm * dm, 4.0 * T * (5 * dm))
+        with fork.side(3):
+            gemm(dqkv, x.reshape(T, dm), dwqkv, 3 * dm, dm, T, lda=3 * dm, ldb=dm, ldc=dm, transA=True, wgrad=True)
+        stage(16, 0.0, 0.0)
+        if _DEFER_WGRAD_JOIN:
+            fork.join_at_end_of_backward((dy2, g2, g1, dx1, gfc, dqkv, hid, x1, heads, x, dw2, dw1, dwfc, dwqkv))
+        else:
+            fork.join()
+        grads = [dwqkv[i * dm:(i + 1) * dm] for i in range(3)] + [dvec[i * dm:(i + 1) * dm] for i in range(3)]
+        o = 3 * dm
+        if has_norm:
+            grads += [dvec[o + i * dk:o + (i + 1) * dk] for i in range(4 * H)]
+        o += 4 * dm
+        grads += [dwfc, dvec[o:o + dm], dw1, dvec[o + dm:o + dm + dff], dw2, dvec[o + dm + dff:o + 2 * dm + dff]]
+        return (dx if ctx.needs_input_grad[0] else None, None, None, None, None, *grads)
 
 
 def encoder_layer(x, pos, params, *, n_head, pos_dim, eps, attention_scale, keep_mask=None, mask_p=0.0,
-                  p_attn_out=0.0, res_sign=1.0, p_ffn=0.0, p_out=0.0):
+                  p_attn_out=0.0, res_sign=1.0, p_ffn=0.0, p_out=0.0, packed=None):
     """Fused Galerkin encoder layer; returns (x_out (B, n, d_model), attention matrix (B, H, d, d))."""
     mask_p = 0.0 if keep_mask is not None else float(mask_p)
     cfg = (int(n_head), int(pos_dim), float(eps), float(attention_scale), mask_p,
            next_seed() if mask_p > 0.0 else 0, float(p_attn_out), next_seed() if p_attn_out > 0.0 else 0,
            float(res_sign), float(p_ffn), next_seed() if p_ffn > 0.0 else 0, float(p_out),
            next_seed() if p_out > 0.0 else 0)
-    return _EncoderLayerFn.apply(x.contiguous(), pos.contiguous(), keep_mask, cfg, *params)
+    return _EncoderLayerFn.apply(x.contiguous(), pos.contiguous(), keep_mask, cfg, packed, *params)
 
 
 # ------------------------------------------------------------------------------------------

@@ -110,15 +110,20 @@ class SimpleTransformerEncoderLayer(nn.Module):
 
 
     # ---- fused path: the whole layer as three tcgen05 kernels (csrc/encoder_fwd.cu) ----
-    def _fused_ok(self, x, pos, weight):
+    def _fused_static_ok(self):
         a = self.attn
-        if GF.get_precision() != 'x3' or weight is not None or self.add_layer_norm or a.attention_type != 'galerkin':
+        if GF.get_precision() != 'x3' or self.add_layer_norm or a.attention_type != 'galerkin':
             return False
-        if a.pos_dim < 1 or pos is None:       # without position columns the reference layer has no `fc` at all
+        if a.pos_dim < 1:                      # without position columns the reference layer has no `fc` at all
             return False
-        if self.ff.act_name != 'relu' or self.ff.lr2.out_features != self.d_model or x.dim() != 3 or not x.is_cuda:
+        if self.ff.act_name != 'relu' or self.ff.lr2.out_features != self.d_model:
             return False
         return GF.encoder_fused_supported(self.d_model, self.n_head, a.pos_dim, self.ff.lr1.out_features)
+
+    def _fused_ok(self, x, pos, weight):
+        if weight is not None or pos is None or x.dim() != 3 or not x.is_cuda:
+            return False
+        return self._fused_static_ok()
 
     def _fused_params(self):
         a = self.attn
@@ -128,6 +133,12 @@ class SimpleTransformerEncoderLayer(nn.Module):
                 ps += [getattr(m, attr) for m in mods]
         ps += [a.fc.weight, a.fc.bias]
         return ps + [self.ff.lr1.weight, self.ff.lr1.bias, self.ff.lr2.weight, self.ff.lr2.bias]
+
+    def prepack(self):
+        """Pack this layer's parameters for the fused kernels now (consumed by the next forward); lets a model pack
+        all its layers up front, off the critical path."""
+        a = self.attn
+        self._prepacked = GF.encoder_pack(self._fused_params(), a.n_head, self.d_model, a.pos_dim, self.ff.lr1.out_features)
 
     def _forward_fused(self, x, pos, p1, p2, sign):
         a = self.attn
@@ -145,11 +156,29 @@ class SimpleTransformerEncoderLayer(nn.Module):
         pf = self.ff.dropout.p if self.training else 0.0
         y, attn_weight = GF.encoder_layer(x, pos, self._fused_params(), n_head=a.n_head, pos_dim=a.pos_dim, eps=a.eps,
                                           attention_scale=1.0 / n, keep_mask=keep, mask_p=mask_p, p_attn_out=p1,
-                                          res_sign=sign, p_ffn=pf, p_out=p2)
+                                          res_sign=sign, p_ffn=pf, p_out=p2, packed=self.__dict__.pop('_prepacked', None))
         a.attn_weight = attn_weight
         if self.attn_weight:
             return y, attn_weight
         return y
+
+
+def prepack_encoder_layers(layers, like, pos, weight=None):
+    """Pack the parameters of every fused encoder layer on an auxiliary stream, so the ten pack launches overlap
+    whatever precedes the encoder stack (the down-scaler); returns the stream the caller must wait on before the first
+    layer runs, or None when nothing was packed."""
+    if weight is not None or pos is None or not like.is_cuda:
+        return None
+    todo = [l for l in layers if isinstance(l, SimpleTransformerEncoderLayer) and l._fused_static_ok()]
+    if not todo:
+        return None
+    main = torch.cuda.current_stream(like.device)
+    side = GF.aux_stream(like.device)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        for l in todo:
+            l.prepack()
+    return side
 
 
 class PointwiseRegressor(nn.Module):
@@ -507,10 +536,13 @@ class FourierTransformer2D(_ConfiguredModel):
         bsz = node.size(0)
         n_s = int(pos.size(1) ** 0.5)
         x_latent, attn_weights = [], []
+        packing = prepack_encoder_layers(self.encoder_layers, node, pos, weight)
         if not self.downscaler_size:
             node = torch.cat([node, pos.contiguous().view(bsz, n_s, n_s, -1)], dim=-1)
         x = self.downscaler(node)
         x = self._drop(x.reshape(bsz, -1, self.n_hidden))
+        if packing is not None:
+            torch.cuda.current_stream(x.device).wait_stream(packing)
         for encoder in self.encoder_layers:
             if self.return_attn_weight:
                 x, w = encoder(x, pos, weight)

@@ -6,7 +6,9 @@
   * the module path: fused layer == per-operator exact-fp32 layer, outputs and every gradient, with ALL dropouts
     active and identical seeds (the fused epilogues draw the same Philox streams as the unfused ones);
   * the oracle at C3 size.
-Tolerances (relative L2, bf16x3 arithmetic ~2^-17 per product): forward 5e-5, gradients 1e-3."""
+Tolerances (relative L2, bf16x3 arithmetic ~2^-17 per product): forward 5e-5, gradients 5e-3 (SURVEY 8c's gradient bar; the
+limit is not the arithmetic (1e-5..1e-4 on smooth paths) but the handful of ReLU gates with |z| ~ 1e-5 |z|_rms that flip
+between any two evaluation orders -- each flip moves one hidden unit's gradient contribution by O(1))."""
 import os
 import sys
 
@@ -23,7 +25,7 @@ import debug_fused as DF          # noqa: E402
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
-FWD_TOL, GRAD_TOL = 5e-5, 1e-3
+FWD_TOL, GRAD_TOL = 5e-5, 5e-3
 
 
 @pytest.fixture(autouse=True)
@@ -34,7 +36,7 @@ def _x3():
 
 
 @pytest.mark.parametrize("B,n,p", [(2, 300, 2), (1, 128, 2), (3, 129, 1), (2, 1849, 2), (1, 57, 2)])
-def test_fused_forward_kernels_against_fp64(B, n, p):
+def test_fused_kernels_against_fp64(B, n, p):
     eps = 1e-6
     P, x, pos, keep = DF.make(B, n, p, seed=B * 1000 + n)
     R = DF.reference(P, x, pos, keep, eps)
@@ -53,6 +55,8 @@ def test_fused_forward_kernels_against_fp64(B, n, p):
     o = DF.run_stage(7, P, x, pos, keep, packed, R, eps)
     for k in ("qkv", "A", "heads", "x1", "hid", "x2"):
         assert rel_l2(o[k], R[k]) < FWD_TOL, k
+    # backward kernels, one at a time on reference inputs, then chained
+    assert DF.check_backward(P, x, pos, keep, packed, R, eps, tol=1e-4)
 
 
 def _layer(dropout, seed=0, residual_type="add"):

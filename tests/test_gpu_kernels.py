@@ -225,10 +225,12 @@ def test_fused_dropout_statistics_and_backward_consistency():
     kept = (y != 0) & (dense > 0)
     frac = kept.sum().item() / (dense > 0).sum().item()
     assert abs(frac - (1 - p)) < 0.01                       # keep probability
-    assert rel_l2(y[kept], dense[kept] / (1 - p)) < TOL     # inverted-dropout scale
+    # the drop probability is quantised to thr / 65536 and the keep scale is its exact inverse complement (unbiased mask)
+    keep_scale = 65536.0 / (65536.0 - round(p * 65536.0))
+    assert rel_l2(y[kept], dense[kept] * keep_scale) < TOL  # inverted-dropout scale
     # backward regenerates the same mask: grad flows only through kept, positive entries
     y.sum().backward()
-    mask = kept.double() / (1 - p)
+    mask = kept.double() * keep_scale
     assert rel_l2(x.grad, mask @ W.detach().double()) < 1e-5
     assert rel_l2(W.grad, mask.t() @ x.detach().double()) < 1e-5
 
