@@ -117,6 +117,17 @@ SIGNATURES = {
                                         c_vp, c_float, c_ull, c_float, c_ull, c_float, c_float, c_float, c_ull,
                                         c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz,
                                         c_int, c_vp]),
+    "gb200_conv3x3_supported": (c_int, [c_int, c_int]),
+    "gb200_conv3x3_pack_bytes": (c_sz, [c_int, c_int, c_int]),
+    "gb200_conv3x3_pack": (c_int, [c_int, c_vp, c_int, c_int, c_int, c_vp, c_vp]),
+    "gb200_conv_split": (c_int, [c_int, c_vp, c_int, c_int, c_int, c_ll, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_float, c_ull,
+                                 c_vp, c_vp]),
+    "gb200_conv3x3": (c_int, [c_int, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_int,
+                              c_int, c_int, c_float, c_ull, c_vp]),
+    "gb200_conv1_fwd": (c_int, [c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_float, c_ull, c_vp]),
+    "gb200_conv1_bwd_workspace_bytes": (c_sz, [c_int]),
+    "gb200_conv1_bwd": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_float, c_vp, c_sz,
+                                c_vp]),
 }
 
 

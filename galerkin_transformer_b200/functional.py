@@ -570,6 +570,101 @@ def interp_bilinear(x, Hout, Wout):
 
 
 # ------------------------------------------------------------------------------------------
+# 3x3 convolution block of the interpolation scalers (csrc/conv.cu)
+# ------------------------------------------------------------------------------------------
+class _Conv3x3BlockFn(torch.autograd.Function):
+    """y = act(dropout_p(conv3x3(x))), x (B, H, W, Cin) channel-last fp32, weight (Cout, Cin, 3, 3), stride 1, padding 1.
+    Forward and input gradient: tcgen05 implicit GEMM in bf16x3 (Cin = 1: streaming stencil); weight gradient: a library
+    convolution-backward call in TF32 (a contraction over all pixels, like every other weight gradient of 'x3' mode)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, act, p, seed):
+        require_cuda_f32(x, weight)
+        lib = _lib.load()
+        B, H, W, Cin = x.shape
+        Cout = weight.shape[0]
+        dev, st = _dev(x), stream_of(x)
+        w = weight.contiguous()
+        y = torch.empty((B, H, W, Cout), dtype=torch.float32, device=x.device)
+        npix = B * H * W
+        z = None
+        if Cin == 1:
+            _launch("conv1_stencil", 18.0 * npix * Cout, 4.0 * npix * (1 + Cout), lib.gb200_conv1_fwd, dev, ptr(x), ptr(w),
+                    ptr(y), B, H, W, Cout, act, p, seed, st)
+        else:
+            CP = 64 * ((Cin + 63) // 64)
+            hi = torch.empty((npix, CP), dtype=torch.bfloat16, device=x.device)
+            lo = torch.empty_like(hi)
+            _launch("conv_split", 4.0 * npix * Cin, 4.0 * npix * (Cin + CP), lib.gb200_conv_split, dev, ptr(x), Cin, 0, Cin,
+                    npix, ptr(hi), ptr(lo), None, 0, 0, 0, 0.0, 0, None, st)
+            wt = torch.empty(lib.gb200_conv3x3_pack_bytes(Cin, Cout, 0), dtype=torch.uint8, device=x.device)
+            _launch("conv_pack", 0.0, 2.0 * wt.numel(), lib.gb200_conv3x3_pack, dev, ptr(w), Cin, Cout, 0, ptr(wt), st)
+            if act == ACT["silu"] and (x.requires_grad or weight.requires_grad):
+                z = torch.empty_like(y)
+            _launch("conv3x3_tc", 18.0 * npix * Cin * Cout, 4.0 * npix * (CP + Cout) + wt.numel(), lib.gb200_conv3x3, dev,
+                    ptr(hi), ptr(lo), Cin, ptr(wt), Cout, B, H, W, ptr(y), Cout, 0, ptr(z), None, 0, 0, act, p, seed, st)
+        ctx.save_for_backward(x, weight, y if z is None else z)
+        ctx.cfg = (act, p, seed)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, yz = ctx.saved_tensors
+        act, p, seed = ctx.cfg
+        lib = _lib.load()
+        B, H, W, Cin = x.shape
+        Cout = weight.shape[0]
+        dev, st = _dev(x), stream_of(x)
+        dy = dy.contiguous()
+        npix = B * H * W
+        w = weight.contiguous()
+        dx = dw = None
+        if Cin == 1:
+            assert act == ACT["relu"], "conv1 backward: ReLU block only"
+            dw = torch.empty_like(w)
+            dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+            wsb = lib.gb200_conv1_bwd_workspace_bytes(Cout)
+            ws = workspace(wsb, x)
+            _launch("conv1_stencil", 36.0 * npix * Cout, 8.0 * npix * Cout, lib.gb200_conv1_bwd, dev, ptr(dy), ptr(yz), ptr(x),
+                    ptr(w), ptr(dx), ptr(dw), B, H, W, Cout, p, ptr(ws), wsb, st)
+            return dx, dw, None, None, None
+        CPo = 64 * ((Cout + 63) // 64)
+        g = torch.empty((B, H, W, Cout), dtype=torch.float32, device=x.device)
+        ghi = torch.empty((npix, CPo), dtype=torch.bfloat16, device=x.device)
+        glo = torch.empty_like(ghi)
+        _launch("conv_split", 6.0 * npix * Cout, 4.0 * npix * (3 * Cout + CPo), lib.gb200_conv_split, dev, ptr(dy), Cout, 0, Cout,
+                npix, ptr(ghi), ptr(glo), ptr(yz), Cout, 0, act, p, seed, ptr(g), st)
+        fork = _Fork(dy)
+        if ctx.needs_input_grad[1]:
+            with fork.side(0):
+                prev = torch.backends.cudnn.allow_tf32
+                torch.backends.cudnn.allow_tf32 = True
+                try:
+                    dw = torch.ops.aten.convolution_backward(g.permute(0, 3, 1, 2), x.permute(0, 3, 1, 2), weight, None, [1, 1],
+                                                             [1, 1], [1, 1], False, [0, 0], 1, [False, True, False])[1]
+                finally:
+                    torch.backends.cudnn.allow_tf32 = prev
+        if ctx.needs_input_grad[0]:
+            wt = torch.empty(lib.gb200_conv3x3_pack_bytes(Cin, Cout, 1), dtype=torch.uint8, device=x.device)
+            _launch("conv_pack", 0.0, 2.0 * wt.numel(), lib.gb200_conv3x3_pack, dev, ptr(w), Cin, Cout, 1, ptr(wt), st)
+            dx = torch.empty_like(x)
+            _launch("conv3x3_tc", 18.0 * npix * Cin * Cout, 4.0 * npix * (CPo + Cin) + wt.numel(), lib.gb200_conv3x3, dev,
+                    ptr(ghi), ptr(glo), Cout, ptr(wt), Cin, B, H, W, ptr(dx), Cin, 0, None, None, 0, 0, 0, 0.0, 0, st)
+        fork.join()
+        return dx, dw, None, None, None
+
+
+def conv3x3_supported(cin, cout):
+    return bool(_lib.load().gb200_conv3x3_supported(int(cin), int(cout)))
+
+
+def conv3x3_block(x, weight, *, act="relu", drop_p=0.0):
+    """x (B, H, W, Cin) channel-last -> act(dropout(conv3x3(x))) (B, H, W, Cout)"""
+    seed = next_seed() if drop_p > 0.0 else 0
+    return _Conv3x3BlockFn.apply(x.contiguous(), weight, ACT[act], float(drop_p), seed)
+
+
+# ------------------------------------------------------------------------------------------
 # Row LayerNorm
 # ------------------------------------------------------------------------------------------
 class _LayerNormFn(torch.autograd.Function):

@@ -282,6 +282,18 @@ class Conv2dResBlock(nn.Module):
         self.add_res = residual
 
     def forward(self, x):
+        conv, drop = self.conv[0], self.conv[1]
+        act = _act_name(self.activation)
+        # 'x3' mode: the library's bf16x3 tensor-core convolution (csrc/conv.cu) with dropout + activation in its epilogue;
+        # 'fp32' / 'tf32' modes: stock cuDNN at that precision
+        if (GF.get_precision() == 'x3' and x.is_cuda and conv.bias is None and conv.kernel_size == (3, 3)
+                and conv.padding == (1, 1) and conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1
+                and isinstance(self.activation, (nn.ReLU, nn.SiLU))
+                and (conv.in_channels > 1 or (act == 'relu' and conv.out_channels % 4 == 0))
+                and GF.conv3x3_supported(conv.in_channels, conv.out_channels)):
+            p = drop.p if self.training else 0.0
+            y = GF.conv3x3_block(x.permute(0, 2, 3, 1), conv.weight, act=act, drop_p=p)
+            return y.permute(0, 3, 1, 2)
         return self.activation(self.conv(x))
 
 

@@ -310,6 +310,29 @@ int gb200_encoder_layer_bwd(int device, const void* packed, int d_model, int n_h
                             float* dqkv, float* dx, float* dvec, float* workspace, size_t workspace_bytes, int stages,
                             void* stream);
 
+/* ------------------------------------------------------------------ scaler convolutions --------
+ * y = act( dropout( conv3x3(x) ) ), stride 1, padding 1, no bias, channel-last (B, H, W, C) fp32: Conv2dResBlock
+ * (libs/layers.py:88-150) as used by Interp2dEncoder (:431-512) and Interp2dUpsample (:624-670).  csrc/conv.cu:
+ * implicit GEMM on tcgen05 in bf16x3 arithmetic; the nine taps are nine shifted 4-D TMA tile loads of the (hi, lo) bf16
+ * images of the input (TMA's out-of-bounds zero fill is the padding).  gb200_conv_split makes the images (and, in
+ * backward mode, applies the activation / dropout derivative first); gb200_conv3x3_pack lays the weights out as operand
+ * tiles for the forward (dgrad = 0) or the input-gradient pass (dgrad = 1: transposed and flipped), which is the same
+ * kernel.  The 1 -> C first convolution is a streaming stencil (gb200_conv1_*; backward for the ReLU block).
+ * The weight gradient of the multi-channel blocks is left to the caller (a library convolution-backward call). */
+int gb200_conv3x3_supported(int Cin, int Cout);
+size_t gb200_conv3x3_pack_bytes(int Cin, int Cout, int dgrad);
+int gb200_conv3x3_pack(int device, const float* w, int Cin, int Cout, int dgrad, void* tiles, void* stream);
+int gb200_conv_split(int device, const float* x, int ldx, int c0, int C, long long npix, void* hi, void* lo, const float* yz,
+                     int ldyz, int yz_c0, int act, float p, unsigned long long seed, float* gout, void* stream);
+int gb200_conv3x3(int device, const void* in_hi, const void* in_lo, int Cin, const void* wtiles, int Cout, int B, int H, int W,
+                  float* out, int ldo, int co0, float* zout, const float* resid, int ldr, int r0, int act, float p,
+                  unsigned long long seed, void* stream);
+int gb200_conv1_fwd(int device, const float* x, const float* w, float* y, int B, int H, int W, int C, int act, float p,
+                    unsigned long long seed, void* stream);
+size_t gb200_conv1_bwd_workspace_bytes(int C);
+int gb200_conv1_bwd(int device, const float* dy, const float* y, const float* x, const float* w, float* dx, float* dw, int B,
+                    int H, int W, int C, float p, float* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
