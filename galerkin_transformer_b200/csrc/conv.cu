@@ -345,30 +345,45 @@ __global__ void __launch_bounds__(256) conv1_dgrad_kernel(Conv1BwdArgs a) {
     }
 }
 
-__global__ void __launch_bounds__(128) conv1_wgrad_kernel(Conv1BwdArgs a) {
-    const int c = threadIdx.x;
+__global__ void __launch_bounds__(256) conv1_wgrad_kernel(Conv1BwdArgs a) {
+    // CTA = a range of pixels; thread = (channel quad, pixel phase): 32 channel quads x 8 phases -> float4 loads of g,
+    // eight independent pixels in flight per quad; the phases are summed through shared memory in fixed order
+    __shared__ float red[8][9][128 + 4];
+    const int cq = threadIdx.x & 31, ph = threadIdx.x >> 5;
+    const int c = cq * 4;
     const long long npix = (long long)a.B * a.H * a.W;
     const long long per = (npix + gridDim.x - 1) / gridDim.x;
     const long long beg = blockIdx.x * per, end = min(npix, beg + per);
-    float acc[9];
+    float acc[9][4];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+    for (int t = 0; t < 9; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
     if (c < a.C) {
-        for (long long px = beg; px < end; ++px) {
-            const float yv = a.y[px * a.C + c];
-            if (yv > 0.f) {
-                const float g = a.dy[px * a.C + c] * a.keep;
-                const int xx = (int)(px % a.W), yy = (int)((px / a.W) % a.H);
+        for (long long px = beg + ph; px < end; px += 8) {
+            const float4 yv = *reinterpret_cast<const float4*>(a.y + px * a.C + c);
+            float4 g = *reinterpret_cast<const float4*>(a.dy + px * a.C + c);
+            g.x = yv.x > 0.f ? g.x * a.keep : 0.f; g.y = yv.y > 0.f ? g.y * a.keep : 0.f;
+            g.z = yv.z > 0.f ? g.z * a.keep : 0.f; g.w = yv.w > 0.f ? g.w * a.keep : 0.f;
+            const int xx = (int)(px % a.W), yy = (int)((px / a.W) % a.H);
 #pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    const int y2 = yy + t / 3 - 1, x2 = xx + t % 3 - 1;
-                    if (y2 >= 0 && y2 < a.H && x2 >= 0 && x2 < a.W)
-                        acc[t] = fmaf(g, a.x[px + (long long)(y2 - yy) * a.W + (x2 - xx)], acc[t]);
-                }
+            for (int t = 0; t < 9; ++t) {
+                const int y2 = yy + t / 3 - 1, x2 = xx + t % 3 - 1;
+                const float xv = (y2 >= 0 && y2 < a.H && x2 >= 0 && x2 < a.W) ? a.x[px + (long long)(y2 - yy) * a.W + (x2 - xx)] : 0.f;
+                acc[t][0] = fmaf(g.x, xv, acc[t][0]); acc[t][1] = fmaf(g.y, xv, acc[t][1]);
+                acc[t][2] = fmaf(g.z, xv, acc[t][2]); acc[t][3] = fmaf(g.w, xv, acc[t][3]);
             }
         }
+    }
 #pragma unroll
-        for (int t = 0; t < 9; ++t) a.dwpart[((long long)blockIdx.x * 9 + t) * a.C + c] = acc[t];
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) red[ph][t][c + i] = acc[t][i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * a.C; i += blockDim.x) {
+        const int t = i / a.C, cc = i % a.C;
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[k][t][cc];
+        a.dwpart[((long long)blockIdx.x * 9 + t) * a.C + cc] = s;
     }
 }
 
@@ -477,7 +492,7 @@ extern "C" size_t gb200_conv1_bwd_workspace_bytes(int C) { return (size_t)148 * 
 extern "C" int gb200_conv1_bwd(int device, const float* dy, const float* y, const float* x, const float* w, float* dx, float* dw,
                                int B, int H, int W, int C, float p, float* workspace, size_t workspace_bytes, void* stream) {
     use_device(device);
-    GB_REQUIRE(dy && y && x && w && dw && workspace && C <= 128, "gb200_conv1_bwd: bad arguments");
+    GB_REQUIRE(dy && y && x && w && dw && workspace && C <= 128 && C % 4 == 0, "gb200_conv1_bwd: bad arguments");
     GB_REQUIRE(workspace_bytes >= gb200_conv1_bwd_workspace_bytes(C), "gb200_conv1_bwd: workspace too small");
     Conv1BwdArgs a;
     a.dy = dy; a.y = y; a.x = x; a.w = w; a.dx = dx; a.dwpart = workspace; a.B = B; a.H = H; a.W = W; a.C = C;
@@ -489,7 +504,7 @@ extern "C" int gb200_conv1_bwd(int device, const float* dy, const float* y, cons
         ++launched;
     }
     const int nparts = 148 * 4;
-    conv1_wgrad_kernel<<<nparts, 128, 0, st>>>(a);
+    conv1_wgrad_kernel<<<nparts, 256, 0, st>>>(a);
     conv1_wgrad_final_kernel<<<(9 * C + 127) / 128, 128, 0, st>>>(workspace, nparts, C, dw);
     return check_launch("gb200_conv1_bwd", launched);
 }

@@ -90,18 +90,19 @@ __device__ __forceinline__ void reduce_attn_partials(const float* __restrict__ p
     float acc[EPT];
 #pragma unroll
     for (int i = 0; i < EPT; ++i) acc[i] = 0.f;
-    for (int k = 0; k < tiles; k += 2) {
+    // four tiles' loads in flight per round (76 independent loads per thread); tile order of the sum is fixed
+    for (int k = 0; k < tiles; k += 4) {
         const float* p0 = pb + (long long)k * ne;
-        const bool two = k + 1 < tiles;
-        float t0[EPT], t1[EPT];
+        float t[4][EPT];
 #pragma unroll
-        for (int i = 0; i < EPT; ++i) {
-            const int e = wt + i * NWORK * 32;
-            t0[i] = e < ne ? __ldg(p0 + e) : 0.f;
-            t1[i] = (two && e < ne) ? __ldg(p0 + ne + e) : 0.f;
-        }
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int i = 0; i < EPT; ++i) acc[i] = (acc[i] + t0[i]) + t1[i];
+            for (int i = 0; i < EPT; ++i) {
+                const int e = wt + i * NWORK * 32;
+                t[j][i] = (k + j < tiles && e < ne) ? __ldg(p0 + (long long)j * ne + e) : 0.f;
+            }
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) acc[i] = (((acc[i] + t[0][i]) + t[1][i]) + t[2][i]) + t[3][i];
     }
 #pragma unroll
     for (int i = 0; i < EPT; ++i) {

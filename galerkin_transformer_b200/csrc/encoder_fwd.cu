@@ -391,18 +391,18 @@ __global__ void __launch_bounds__(THREADS, 1) enc_attn_kernel(const __grid_const
 #pragma unroll
             for (int i = 0; i < EPT; ++i) acc[i] = 0.f;
             const int ne = NH * dd;
-            for (int k = 0; k < a.tiles; k += 2) {
+            for (int k = 0; k < a.tiles; k += 4) {
                 const float* p0 = pb + (long long)k * ne;
-                const bool two = k + 1 < a.tiles;
-                float t0[EPT], t1[EPT];
+                float t[4][EPT];
 #pragma unroll
-                for (int i = 0; i < EPT; ++i) {
-                    const int e = wt + i * NWORK * 32;
-                    t0[i] = e < ne ? __ldg(p0 + e) : 0.f;
-                    t1[i] = (two && e < ne) ? __ldg(p0 + ne + e) : 0.f;
-                }
+                for (int j = 0; j < 4; ++j)
 #pragma unroll
-                for (int i = 0; i < EPT; ++i) acc[i] = (acc[i] + t0[i]) + t1[i];
+                    for (int i = 0; i < EPT; ++i) {
+                        const int e = wt + i * NWORK * 32;
+                        t[j][i] = (k + j < a.tiles && e < ne) ? __ldg(p0 + (long long)j * ne + e) : 0.f;
+                    }
+#pragma unroll
+                for (int i = 0; i < EPT; ++i) acc[i] = (((acc[i] + t[0][i]) + t[1][i]) + t[2][i]) + t[3][i];
             }
 #pragma unroll
             for (int i = 0; i < EPT; ++i) {

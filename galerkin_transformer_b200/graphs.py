@@ -23,7 +23,7 @@ class GraphedStep:
         loss = graphed(node, pos, grid, y)      # copies inputs into the static buffers, replays
     """
 
-    def __init__(self, step_fn, example_inputs, params, warmup=3, batch_streams=1):
+    def __init__(self, step_fn, example_inputs, params, warmup=3, batch_streams=1, post_backward=None):
         """batch_streams = k > 1: the static inputs are split into k equal chunks along dim 0 and step_fn runs on each
         chunk on its own stream (forward AND, because autograd replays a node on its forward stream, backward), the
         k losses are averaged.  For per-sample-independent models with a batch-mean loss (every model of this
@@ -52,6 +52,9 @@ class GraphedStep:
             GF.advance_rng()
             self.static_loss = self._loss()
             self.static_loss.backward()
+            self.static_grads = [p.grad for p in self.params]
+            if post_backward is not None:        # e.g. FlatGradBucket.pack: the gradient bucket is filled inside the graph
+                post_backward(self.static_grads)
         self.static_grads = [p.grad for p in self.params]
 
     def _eager_step(self):

@@ -60,6 +60,18 @@ class FlatGradBucket:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
             self.flat.div_(self.world_size())
 
+    def all_reduce_packed(self):
+        """The collective alone, for a bucket that something else already filled -- e.g. the last node of a captured CUDA
+        graph (graphs.GraphedStep(post_backward=bucket.pack)): enqueue this right after `graph.replay()` and only the
+        NVLink transfer itself stays on the critical path (no pack launch, no host gap)."""
+        if not dist.is_initialized() or self.world_size() == 1:
+            return
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat.div_(self.world_size())
+
 
 def shard_batch(tensors, rank, world_size):
     """Contiguous equal shards of the leading (batch) axis."""

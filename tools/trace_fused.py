@@ -34,11 +34,52 @@ NAMES = {
 }
 
 
+BNAMES = {
+    1: {0: "entry", 9: "worker0: dy landed", 10: "worker0: mask+split done", 4: "mma: g2 ready", 5: "mma: g1_pre MMAs issued",
+        11: "worker0: g1_pre block ready", 13: "worker0: g1 epilogue done", 8: "mma: dx1 MMAs issued", 15: "worker0: dx1 accum ready",
+        16: "worker0: dx1 + partials stored", 17: "exit"},
+    2: {0: "entry", 9: "worker0: dx1 landed", 10: "worker0: g_fc split done", 11: "worker0: Q split + pos block done",
+        4: "mma: g_fc ready", 14: "worker0: dheads accum ready", 15: "worker0: A^T operand + dheads operand written",
+        7: "mma: operands handed over", 8: "mma: dQ/G/Gp issued", 16: "worker0: all accum ready", 17: "worker0: stored", 18: "exit"},
+    4: {0: "entry", 10: "worker0: G partials reduced", 11: "worker0: operands built + K,V split", 4: "mma: operands ready",
+        8: "mma: issued", 14: "worker0: accum ready", 17: "worker0: LN bwd + stores done", 18: "exit"},
+    8: {0: "entry", 11: "worker0: 3 blocks split", 8: "mma: all issued", 14: "worker0: accum ready", 17: "worker0: stored", 18: "exit"},
+}
+
+
+def trace_backward(args, P, x, pos, keep, packed, lib, grid):
+    B, n, p = args.B, args.n, 2
+    T, d = B * n, 32 + p
+    R = dict(qkv=torch.randn(T, 384, device="cuda"), rk=torch.rand(T, 4, device="cuda"), rv=torch.rand(T, 4, device="cuda"),
+             A=torch.randn(B, 4, d, d, device="cuda"), hid=torch.randn(T, 256, device="cuda"))
+    RB = dict(dx1=torch.randn(T, 128, device="cuda"), dqkv=torch.randn(T, 384, device="cuda"), Graw=torch.randn(B, 4, d, d, device="cuda"))
+    dy = torch.randn(B, n, 128, device="cuda")
+    buf = torch.zeros(grid * 32, dtype=torch.int64, device="cuda")
+    for stage, name in ((1, "enc_ffn_bwd_kernel"), (2, "enc_attn_bwd_kernel"), (4, "enc_kv_bwd_kernel"), (8, "enc_dx_kernel")):
+        for _ in range(2):
+            DF.run_bwd_stage(stage, P, x, pos, keep, packed, R, RB, dy, 1e-6)
+        buf.zero_()
+        torch.cuda.synchronize()
+        lib.gb200_encoder_bwd_set_trace(buf.data_ptr())
+        DF.run_bwd_stage(stage, P, x, pos, keep, packed, R, RB, dy, 1e-6)
+        lib.gb200_encoder_bwd_set_trace(None)
+        t = buf.view(grid, 32).cpu()
+        print(f"== {name}: {grid} CTAs (inputs L2-warm)")
+        rel = (t - t[:, :1]).double() / args.mhz
+        for slot, label in sorted(BNAMES[stage].items(), key=lambda kv: rel[:, kv[0]].median().item()):
+            col = rel[:, slot]
+            if (t[:, slot] == 0).all():
+                continue
+            print(f"   {col.median().item():8.2f} us (max {col.max().item():8.2f})  [{slot:2d}] {label}")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--B", type=int, default=8)
     ap.add_argument("--n", type=int, default=1849)
     ap.add_argument("--mhz", type=float, default=1965.0)
+    ap.add_argument("--bwd", action="store_true")
+    ap.add_argument("--warm", action="store_true", help="do not flush L2 before the traced launch")
     args = ap.parse_args()
     B, n, p = args.B, args.n, 2
     eps = 1e-6
@@ -51,10 +92,13 @@ def main():
     grid = B * ((n + 127) // 128)
     buf = torch.zeros(grid * 32, dtype=torch.int64, device="cuda")
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+    if args.bwd:
+        return trace_backward(args, P, x, pos, keep, packed, lib, grid)
     for stage, name in ((1, "enc_qkv_kernel"), (2, "enc_attn_kernel"), (4, "enc_ffn_kernel")):
         for _ in range(2):
             DF.run_stage(stage, P, x, pos, keep, packed, R, eps)
-        flush.fill_(1.0)
+        if not args.warm:
+            flush.fill_(1.0)
         buf.zero_()
         torch.cuda.synchronize()
         lib.gb200_encoder_set_trace(buf.data_ptr())
