@@ -53,6 +53,7 @@ SIGNATURES = {
                            c_vp, c_int, c_float, c_int, c_int, c_vp, c_sz, c_vp]),
     "gb200_gemm_tc_supported": (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int]),
     "gb200_gemm_tc_suggest_ksplit": (c_int, [c_int] * 3),
+    "gb200_gemm_tc_split_next": (c_int, [c_int]),
     "gb200_gemm_tc_set_trace": (c_int, [c_vp]),
     "gb200_gemm_tc": (c_int, [c_int, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_int,
                               c_float, c_vp, c_int, c_vp, c_int, c_float, c_ull, c_vp, c_int, c_float, c_int,

@@ -36,10 +36,15 @@ constexpr int TC_BM = 128, TC_BK = 32, TC_THREADS = 192;
 #ifndef GB200_TC_STAGES_NARROW
 #define GB200_TC_STAGES_NARROW 4
 #endif
-template <int BN> __host__ __device__ constexpr int tc_stages() { return BN == 192 ? 2 : (BN <= 64 ? GB200_TC_STAGES_NARROW : 3); }
+// SPLIT ("3xTF32"): every operand tile also keeps its TF32 residual lo = rna(x - hi) in a second buffer and each k-step
+// issues hi.hi + hi.lo + lo.hi -- fp32-grade products (2^-22) for the forward / input-gradient GEMMs of 'x3' mode that no
+// fused kernel covers; stages are twice as large, so the ring is one stage shorter
+template <int BN, bool SPLIT = false> __host__ __device__ constexpr int tc_stages() {
+    return SPLIT ? (BN <= 64 ? 3 : 2) : (BN == 192 ? 2 : (BN <= 64 ? GB200_TC_STAGES_NARROW : 3));
+}
 template <int BN> __host__ __device__ constexpr int tc_tmem_cols() { return BN == 192 ? 256 : BN; }     // power of two >= 32
-template <int BN> __host__ __device__ constexpr int tc_smem_bytes() {
-    constexpr int ring = tc_stages<BN>() * (TC_BM * TC_BK * 4 + BN * TC_BK * 4);
+template <int BN, bool SPLIT = false> __host__ __device__ constexpr int tc_smem_bytes() {
+    constexpr int ring = tc_stages<BN, SPLIT>() * (SPLIT ? 2 : 1) * (TC_BM * TC_BK * 4 + BN * TC_BK * 4);
     constexpr int staging = TC_BM * (BN + 4) * 4;                                   // epilogue reuses the ring
     return (ring > staging ? ring : staging) + 1024 + 256;
 }
@@ -161,17 +166,18 @@ __device__ __forceinline__ void tc_epilogue_vec4(const TcArgs& g, const float* _
     }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool SPLIT = false>
 __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
                                                              const __grid_constant__ CUtensorMap mapB, TcArgs g) {
     constexpr int A_BYTES = TC_BM * TC_BK * 4;          // 16 KB
     constexpr int B_BYTES = BN * TC_BK * 4;
-    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr int TC_STAGES = tc_stages<BN>();
+    constexpr int TILE_PAIR = A_BYTES + B_BYTES;        // what TMA lands per k-block
+    constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * TILE_PAIR;   // SPLIT: [A hi | B hi | A lo | B lo]
+    constexpr int TC_STAGES = tc_stages<BN, SPLIT>();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by SWIZZLE_128B atoms
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + tc_smem_bytes<BN>() - 1024 - 256);   // past ring AND staging
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + tc_smem_bytes<BN, SPLIT>() - 1024 - 256);   // past ring AND staging
     uint64_t* empty_bar = full_bar + TC_STAGES;
     uint64_t* conv_bar = empty_bar + TC_STAGES;
     uint64_t* tmem_full = conv_bar + TC_STAGES;
@@ -220,7 +226,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t* sa = smem + s * STAGE_BYTES;
                 uint8_t* sb = sa + A_BYTES;
-                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                mbar_expect_tx(&full_bar[s], TILE_PAIR);
                 const int k0 = kbeg + kb * TC_BK;
                 if (!A_MN) {
                     tma_load_2d(sa, &mapA, &full_bar[s], k0, m0);                    // box {32 k, 128 m}
@@ -247,7 +253,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % TC_STAGES;
                 const uint32_t ph = (kb / TC_STAGES) & 1;
-                mbar_wait(g.truncate ? &full_bar[s] : &conv_bar[s], ph);   // tile landed (TMA) [and rounded to TF32]
+                mbar_wait((g.truncate && !SPLIT) ? &full_bar[s] : &conv_bar[s], ph);   // tile landed (TMA) [and rounded to TF32]
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
                 const uint32_t sb = sa + A_BYTES;
@@ -260,6 +266,13 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
                     const uint64_t ad = A_MN ? umma_desc<1>(sa + k * 1024, 4096, 512) : umma_desc<2>(sa + k * 32, 16, 1024);
                     const uint64_t bd = B_MN ? umma_desc<1>(sb + k * 1024, 4096, 512) : umma_desc<2>(sb + k * 32, 16, 1024);
                     tc_mma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0);
+                    if (SPLIT) {
+                        const uint32_t la = sa + TILE_PAIR, lb = sb + TILE_PAIR;
+                        const uint64_t adl = A_MN ? umma_desc<1>(la + k * 1024, 4096, 512) : umma_desc<2>(la + k * 32, 16, 1024);
+                        const uint64_t bdl = B_MN ? umma_desc<1>(lb + k * 1024, 4096, 512) : umma_desc<2>(lb + k * 32, 16, 1024);
+                        tc_mma_tf32(tmem_base, ad, bdl, idesc, 1u);
+                        tc_mma_tf32(tmem_base, adl, bd, idesc, 1u);
+                    }
                 }
                 tc_commit(&empty_bar[s]);        // frees the stage once these MMAs have read it
             }
@@ -274,7 +287,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
         // systematic -1e-3 relative bias per product); rounding makes the error zero-mean like cuBLAS TF32.
         {
             const int ct = threadIdx.x - 64;     // 0..127
-            for (int kb = 0; kb < (g.truncate ? 0 : nkb); ++kb) {
+            for (int kb = 0; kb < ((g.truncate && !SPLIT) ? 0 : nkb); ++kb) {
                 const int s = kb % TC_STAGES;
                 const uint32_t ph = (kb / TC_STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
@@ -282,7 +295,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
                 if (ct == 0 && kb == nkb - 1) tc_stamp(g, 3);                // last tile landed
                 float4* tile = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
 #pragma unroll 4
-                for (int i = ct; i < STAGE_BYTES / 16; i += 128) {
+                for (int i = ct; i < TILE_PAIR / 16; i += 128) {
                     float4 v = tile[i];
                     uint32_t x, y, z, w;
                     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(x) : "f"(v.x));
@@ -291,6 +304,15 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
                     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(w) : "f"(v.w));
                     tile[i] = make_float4(__uint_as_float(x), __uint_as_float(y), __uint_as_float(z),
                                           __uint_as_float(w));
+                    if (SPLIT) {       // residual, itself rounded to TF32 (same swizzled position in the lo buffer)
+                        uint32_t a, b, c, d;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a) : "f"(v.x - __uint_as_float(x)));
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(v.y - __uint_as_float(y)));
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(c) : "f"(v.z - __uint_as_float(z)));
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(d) : "f"(v.w - __uint_as_float(w)));
+                        tile[i + TILE_PAIR / 16] = make_float4(__uint_as_float(a), __uint_as_float(b), __uint_as_float(c),
+                                                               __uint_as_float(d));
+                    }
                 }
                 // generic-proxy writes -> visible to the tensor core's async-proxy reads
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -669,16 +691,16 @@ static bool make_map(CUtensorMap* m, const float* base, long long inner, long lo
     return r == CUDA_SUCCESS;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool SPLIT = false>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& g, cudaStream_t st) {
-    constexpr int smem = tc_smem_bytes<BN>();
+    constexpr int smem = tc_smem_bytes<BN, SPLIT>();
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         configured = true;
     }
     dim3 grid(cdiv(g.N, BN), cdiv(g.M, TC_BM), g.ksplit);
-    launch_pdl(gemm_tc_kernel<BN, A_MN, B_MN>, grid, TC_THREADS, smem, st, ma, mb, g);
+    launch_pdl(gemm_tc_kernel<BN, A_MN, B_MN, SPLIT>, grid, TC_THREADS, smem, st, ma, mb, g);
     return 0;
 }
 
@@ -752,6 +774,14 @@ extern "C" int gb200_gemm_tc_set_trace(unsigned long long* device_buffer) {
 }
 
 static thread_local HeadNormFusion g_hn = {0, 0, 0, 0, 0.f, {nullptr, nullptr}};
+static thread_local int g_split_next = 0;
+}
+
+/* The NEXT gb200_gemm_tc / gb200_gemm_tc_gated call on this thread runs in split ("3xTF32") arithmetic: each product is
+ * hi.hi + hi.lo + lo.hi of the TF32 two-term split of its fp32 operands (~2^-22 relative).  One-shot. */
+extern "C" int gb200_gemm_tc_split_next(int on) {
+    g_split_next = on;
+    return 0;
 }
 
 extern "C" int gb200_gemm_tc(int device, const float* A, int lda, int transA, const float* B, int ldb, int transB,
@@ -760,6 +790,8 @@ extern "C" int gb200_gemm_tc(int device, const float* A, int lda, int transA, co
                              float rscale, int accumulate, int ksplit, float* workspace, size_t workspace_bytes,
                              void* stream) {
     use_device(device);
+    const bool split = g_split_next != 0;      // one-shot, consumed even if this call fails validation
+    g_split_next = 0;
     GB_REQUIRE(A && B && C, "gb200_gemm_tc: null operand");
     GB_REQUIRE(gb200_gemm_tc_supported(A, lda, B, ldb, M, N, K),
                "gb200_gemm_tc: unsupported shape/alignment (M=%d N=%d K=%d lda=%d ldb=%d); use gb200_gemm", M, N, K,
@@ -794,7 +826,7 @@ extern "C" int gb200_gemm_tc(int device, const float* A, int lda, int transA, co
     GB_REQUIRE(!g.ep.hn_dk || (g.vec4 && g.ksplit == 1), "gb200_gemm_tc: fused head-norm needs the float4 epilogue");
     static const int use_persistent = env_int("GB200_TC_PERSISTENT", 0);   // measured equal/slower in the full step
     const bool persistent = use_persistent && g.ksplit == 1 && !g.ep.hn_dk && !g.ep.G;
-    if (bn == 192 && (persistent || g.ep.hn_dk)) bn = 128;
+    if (bn == 192 && (persistent || g.ep.hn_dk || split)) bn = 128;
     CUtensorMap ma, mb;
     const CUtensorMapSwizzle SWK = CU_TENSOR_MAP_SWIZZLE_128B, SWMN = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
     bool ok = a_mn ? make_map(&ma, A, M, K, lda, 32, 32, SWMN) : make_map(&ma, A, K, M, lda, 32, TC_BM, SWK);
@@ -817,7 +849,19 @@ extern "C" int gb200_gemm_tc(int device, const float* A, int lda, int transA, co
             else launch_tc<BNV, true, true>(ma, mb, g, st);                                       \
         }                                                                                         \
     } while (0)
-    if (bn == 192) {
+    if (split && !persistent) {
+#define TC_SPLIT(BNV)                                                                  \
+    do {                                                                               \
+        if (!a_mn && !b_mn) launch_tc<BNV, false, false, true>(ma, mb, g, st);         \
+        else if (!a_mn && b_mn) launch_tc<BNV, false, true, true>(ma, mb, g, st);      \
+        else if (a_mn && !b_mn) launch_tc<BNV, true, false, true>(ma, mb, g, st);      \
+        else launch_tc<BNV, true, true, true>(ma, mb, g, st);                          \
+    } while (0)
+        if (bn == 128) TC_SPLIT(128);
+        else if (bn == 64) TC_SPLIT(64);
+        else TC_SPLIT(32);
+#undef TC_SPLIT
+    } else if (bn == 192) {
         if (!a_mn && !b_mn) launch_tc<192, false, false>(ma, mb, g, st);
         else if (!a_mn && b_mn) launch_tc<192, false, true>(ma, mb, g, st);
         else if (a_mn && !b_mn) launch_tc<192, true, false>(ma, mb, g, st);

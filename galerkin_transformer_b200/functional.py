@@ -49,6 +49,7 @@ def get_precision():
 
 torch.backends.cudnn.allow_tf32 = _PRECISION == "tf32"
 
+_SPLIT_MIN_FLOPS = float(os.environ.get("GB200_SPLIT_MIN_GFLOP", "0.5")) * 1e9   # measured: C5's 0.15 GFLOP GEMMs lose, C3's 1.3 win
 _seed_lock = threading.Lock()
 _seed_counter = 0
 
@@ -223,8 +224,12 @@ def gemm(A, B, C, M, N, K, *, lda, ldb, ldc, transA=False, transB=False, alpha=1
     pa, pb = ptr(A) + 4 * a_off, ptr(B) + 4 * b_off
     nbytes = 4.0 * (M * K + K * N + M * N * (1 + (residual is not None) + (zout is not None) + (gate is not None)))
     lay = ("t" if transA else "n") + ("t" if transB else "n")
-    use_tc = (_PRECISION == "tf32" or (_PRECISION == "x3" and wgrad)) \
-        and lib.gb200_gemm_tc_supported(pa, lda, pb, ldb, M, N, K)
+    use_tc = _PRECISION in ("tf32", "x3") and lib.gb200_gemm_tc_supported(pa, lda, pb, ldb, M, N, K)
+    if use_tc and _PRECISION == "x3" and not wgrad:
+        if 2.0 * M * N * K < _SPLIT_MIN_FLOPS:  # small problems: the exact SIMT kernel has the shorter fixed latency
+            use_tc = False
+        else:
+            lib.gb200_gemm_tc_split_next(1)    # forward / input-gradient GEMM outside the fused kernels: 3xTF32
     if gate is not None:
         assert bias is None and act == 0 and zout is None and residual is None and not accumulate
         if ksplit is None:

@@ -72,6 +72,10 @@ int gb200_gemm(int device, const float* A, int lda, int transA, const float* B, 
  * aligned operands with lda, ldb multiples of 4 and N, K >= 8 (gb200_gemm_tc_supported); otherwise call
  * gb200_gemm.  Relative error ~4e-4 per contraction (TF32), see DESIGN.md. */
 int gb200_gemm_tc_supported(const float* A, int lda, const float* B, int ldb, int M, int N, int K);
+/* One-shot: the next gb200_gemm_tc / gb200_gemm_tc_gated call of this thread runs in split ("3xTF32") arithmetic -- each
+ * product is hi.hi + hi.lo + lo.hi of the two-term TF32 split of its fp32 operands (~2^-22 relative error): the tensor-core
+ * path of the forward / input-gradient GEMMs in 'x3' precision mode where no fused kernel applies. */
+int gb200_gemm_tc_split_next(int on);
 int gb200_gemm_tc_suggest_ksplit(int M, int N, int K);
 /* Diagnostics: when `device_buffer` is non-null every CTA of subsequent gb200_gemm_tc launches writes eight
  * %globaltimer stamps (entry, setup done, first/last tile landed, last tile rounded, accumulator complete,

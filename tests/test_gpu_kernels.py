@@ -427,3 +427,24 @@ def test_spectral_conv_forward_backward(shape, Co, m, act, prec):
         gtol = 3e-2
     for g, r in zip(grads, gr):
         assert rel_l2(g, r) < gtol
+
+
+@pytest.mark.parametrize("tA,tB", [(False, True), (False, False), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(300, 128, 96), (1000, 32, 128), (257, 136, 40), (4096, 128, 32)])
+def test_gemm_split_tf32_is_fp32_grade(M, N, K, tA, tB):
+    """'x3' mode outside the fused kernels: tcgen05 GEMM with the two-term TF32 split (hi.hi + hi.lo + lo.hi), all four
+    operand layouts, with the fused epilogue -- fp32-grade products (<= 5e-6), against 5e-4 for single-pass TF32."""
+    GF.set_precision("x3")
+    A = rn(K, M, seed=1) if tA else rn(M, K, seed=1)
+    B = rn(N, K, seed=2) if tB else rn(K, N, seed=2)
+    bias, R = rn(N, seed=3), rn(M, N, seed=4)
+    C = torch.empty(M, N, device=DEV)
+    GF.gemm(A, B, C, M, N, K, lda=A.shape[1], ldb=B.shape[1], ldc=N, transA=tA, transB=tB, bias=bias, act=2,
+            residual=R, ldr=N, rscale=0.5)
+    z = (A.double().t() if tA else A.double()) @ (B.double().t() if tB else B.double()) + bias.double()
+    ref = R.double() + 0.5 * torch.nn.functional.silu(z)
+    assert rel_l2(C, ref) < 5e-6, rel_l2(C, ref)
+    Cw = torch.empty(M, N, device=DEV)
+    GF.gemm(A, B, Cw, M, N, K, lda=A.shape[1], ldb=B.shape[1], ldc=N, transA=tA, transB=tB, wgrad=True)   # single-pass TF32
+    plain = (A.double().t() if tA else A.double()) @ (B.double().t() if tB else B.double())
+    assert rel_l2(Cw, plain) < 2e-3, rel_l2(Cw, plain)      # (unaligned leading dimensions fall back to the exact kernel)
