@@ -1,0 +1,6 @@
+"""The reference's own `libs/ft.py` (out of the hot path; re-exported when the reference sources are available)."""
+from galerkin_transformer import export, load_reference_module
+
+_ref = load_reference_module("ft")
+if _ref is not None:
+    export(globals(), _ref)

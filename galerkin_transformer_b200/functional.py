@@ -61,7 +61,8 @@ def next_seed():
     with _seed_lock:
         _seed_counter += 1
         c = _seed_counter
-    return (torch.initial_seed() * 0x9E3779B97F4A7C15 + c * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
+    # 63 bits: the value travels through autograd.Function arguments, which profilers convert to int64
+    return (torch.initial_seed() * 0x9E3779B97F4A7C15 + c * 0xD1B54A32D192ED03) & 0x7FFFFFFFFFFFFFFF
 
 
 def _dev(t):
