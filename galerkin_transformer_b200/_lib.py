@@ -39,6 +39,12 @@ class EncoderParams(ctypes.Structure):
 
 _ENCP = ctypes.POINTER(EncoderParams)
 
+
+class WgradProblem(ctypes.Structure):
+    """mirror of gb200_wgrad_problem"""
+    _fields_ = [("G", c_vp), ("ldg", c_int), ("X", c_vp), ("ldx", c_int), ("dW", c_vp), ("ldw", c_int), ("M", c_int),
+                ("N", c_int), ("T", c_ll)]
+
 # name -> (restype, argtypes); must list every symbol of include/galerkin_b200.h
 SIGNATURES = {
     "gb200_version": (c_int, []),
@@ -54,6 +60,8 @@ SIGNATURES = {
     "gb200_gemm_tc_supported": (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int]),
     "gb200_gemm_tc_suggest_ksplit": (c_int, [c_int] * 3),
     "gb200_gemm_tc_split_next": (c_int, [c_int]),
+    "gb200_gemm_tc_wgrad_group_workspace_bytes": (c_sz, [c_int, ctypes.POINTER(WgradProblem)]),
+    "gb200_gemm_tc_wgrad_group": (c_int, [c_int, c_int, ctypes.POINTER(WgradProblem), c_vp, c_sz, c_vp]),
     "gb200_gemm_tc_set_trace": (c_int, [c_vp]),
     "gb200_gemm_tc": (c_int, [c_int, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_int,
                               c_float, c_vp, c_int, c_vp, c_int, c_float, c_ull, c_vp, c_int, c_float, c_int,

@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(THREADS, 1) enc_ffn_bwd_kernel(const __grid_co
     }
     if (threadIdx.x == 0) { trace_entry(); trace(0); }
     const uint32_t tmem = tmem_alloc_512(&bar->tmem_slot, warp);
+    grid_dep_sync();
     constexpr int DX_COL = 256, DB2_COL = 384, DB1A_COL = 400, DB1B_COL = 416;
 
     if (warp == 0) {
@@ -346,6 +347,7 @@ __global__ void __launch_bounds__(THREADS, 1) enc_attn_bwd_kernel(const __grid_c
     }
     if (threadIdx.x == 0) { trace_entry(); trace(0); }
     const uint32_t tmem = tmem_alloc_512(&bar->tmem_slot, warp);
+    grid_dep_sync();
     constexpr int DQ_COL = 192, DBFC_COL = 320, GP1_COL = 336, GP2_COL = 352;
     constexpr uint32_t BQH = 8192;                             // per-head A_h^T image: hi 4 KB | lo 4 KB
 
@@ -588,6 +590,7 @@ __global__ void __launch_bounds__(THREADS, 1) enc_kv_bwd_kernel(const __grid_con
     }
     if (threadIdx.x == 0) { trace_entry(); trace(0); }
     const uint32_t tmem = tmem_alloc_512(&bar->tmem_slot, warp);
+    grid_dep_sync();
     constexpr int DV_COL = 0, DK_COL = 128;
 
     if (warp == 0) {
@@ -775,6 +778,7 @@ __global__ void __launch_bounds__(THREADS, 1) enc_dx_kernel(const __grid_constan
     }
     if (threadIdx.x == 0) { trace_entry(); trace(0); }
     const uint32_t tmem = tmem_alloc_512(&bar->tmem_slot, warp);
+    grid_dep_sync();
     constexpr int DB_COL = 128;
 
     if (warp == 0) {
@@ -945,7 +949,7 @@ extern "C" int gb200_encoder_layer_bwd(int device, const void* packed, int d_mod
         a.w2t = wt + (size_t)TS_W2T * TILE_BYTES; a.w1t = wt + (size_t)TS_W1T * TILE_BYTES; a.dy = dy; a.hid = hidden;
         a.g2 = p_out > 0.f ? g2 : nullptr; a.g1 = g1; a.dx1 = dx1; a.part = part; a.p2 = p_out; a.pf = p_ffn; a.seed2 = seed_out;
         a.seed_off = rng_offset_ptr(); a.B = B; a.n = n; a.tiles = tiles;
-        enc_ffn_bwd_kernel<<<B * tiles, THREADS, FB_SMEM, st>>>(m, a);
+        launch_enc(enc_ffn_bwd_kernel, B * tiles, FB_SMEM, st, m, a);
         ++launched;
     }
     if (stages & 2) {
@@ -956,7 +960,7 @@ extern "C" int gb200_encoder_layer_bwd(int device, const void* packed, int d_mod
         a.fct = wt + (size_t)TS_FCT * TILE_BYTES; a.dx1 = dx1; a.gfc = need_gfc ? gfc : nullptr; a.p1 = p_attn_out; a.sign = res_sign;
         a.seed1 = seed_attn_out; a.seed_off = rng_offset_ptr(); a.attn = attn; a.pos = pos; a.dqkv = dqkv; a.gpart = gpart;
         a.part = part; a.B = B; a.n = n; a.p = pos_dim; a.tiles = tiles;
-        enc_attn_bwd_kernel<<<B * tiles, THREADS, AB_SMEM, st>>>(mdx, mq, a);
+        launch_enc(enc_attn_bwd_kernel, B * tiles, AB_SMEM, st, mdx, mq, a);
         ++launched;
     }
     if (stages & 4) {
@@ -966,7 +970,7 @@ extern "C" int gb200_encoder_layer_bwd(int device, const void* packed, int d_mod
         a.gpart = gpart; a.keep_mask = keep_mask; a.mask_p = keep_mask ? 0.f : mask_p; a.scale = attn_scale; a.mask_seed = mask_seed;
         a.seed_off = rng_offset_ptr(); a.vec = vec; a.pos = pos; a.qkv = qkv; a.rstd_k = rstd_k; a.rstd_v = rstd_v; a.dqkv = dqkv;
         a.part = part; a.B = B; a.n = n; a.p = pos_dim; a.tiles = tiles; a.has_norm = has_norm;
-        enc_kv_bwd_kernel<<<B * tiles, THREADS, KV_SMEM, st>>>(mq, a);
+        launch_enc(enc_kv_bwd_kernel, B * tiles, KV_SMEM, st, mq, a);
         ++launched;
     }
     if (stages & 8) {
@@ -974,7 +978,7 @@ extern "C" int gb200_encoder_layer_bwd(int device, const void* packed, int d_mod
         GB_REQUIRE(make_tile_map(&mg, dqkv, 3 * DM, n, B), "gb200_encoder_layer_bwd: tensor map (dqkv) failed");
         DxArgs a;
         a.qkvt = wt + (size_t)TS_QKVT * TILE_BYTES; a.dx1 = dx1; a.dx = dx; a.part = part; a.B = B; a.n = n; a.tiles = tiles;
-        enc_dx_kernel<<<B * tiles, THREADS, DX_SMEM, st>>>(mg, a);
+        launch_enc(enc_dx_kernel, B * tiles, DX_SMEM, st, mg, a);
         ++launched;
     }
     if (stages & 16) {

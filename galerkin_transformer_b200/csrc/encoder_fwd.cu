@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(THREADS, 1) enc_qkv_kernel(const __grid_consta
     }
     if (threadIdx.x == 0) { trace_entry(); trace(0); }
     const uint32_t tmem = tmem_alloc_512(&bar->tmem_slot, warp);
+    grid_dep_sync();
     if (threadIdx.x == 0) trace(1);
 
     if (warp == 0) {
@@ -319,6 +320,7 @@ __global__ void __launch_bounds__(THREADS, 1) enc_attn_kernel(const __grid_const
     }
     if (threadIdx.x == 0) { trace_entry(); trace(0); }
     const uint32_t tmem = tmem_alloc_512(&bar->tmem_slot, warp);
+    grid_dep_sync();
     if (threadIdx.x == 0) trace(1);
     constexpr uint32_t BAC = HP * 128;                         // one [48 x 64] chunk image of B_a
     constexpr int DB_COL = 4 * HP;                             // fc accumulator columns 192..319
@@ -546,6 +548,7 @@ __global__ void __launch_bounds__(THREADS, 1) enc_ffn_kernel(const __grid_consta
     }
     if (threadIdx.x == 0) { trace_entry(); trace(0); }
     const uint32_t tmem = tmem_alloc_512(&bar->tmem_slot, warp);
+    grid_dep_sync();
     if (threadIdx.x == 0) trace(1);
     constexpr int DY_COL = 256;
 
@@ -844,7 +847,7 @@ extern "C" int gb200_encoder_layer_fwd(int device, const void* packed, int d_mod
         a.wtiles = wt + (size_t)TS_QKV * TILE_BYTES; a.vec = vec; a.pos = pos; a.qkv = qkv; a.rstd_k = rstd_k;
         a.rstd_v = rstd_v; a.part = workspace; a.B = B; a.n = n; a.p = pos_dim; a.tiles = tiles; a.has_norm = has_norm;
         a.eps = eps;
-        enc_qkv_kernel<<<B * tiles, THREADS, QKV_SMEM, st>>>(mx, a);
+        launch_enc(enc_qkv_kernel, B * tiles, QKV_SMEM, st, mx, a);
         ++launched;
     }
     if (stages & 2) {
@@ -855,7 +858,7 @@ extern "C" int gb200_encoder_layer_fwd(int device, const void* packed, int d_mod
         a.mask_p = keep_mask ? 0.f : mask_p; a.mask_seed = mask_seed; a.seed_off = rng_offset_ptr(); a.scale = attn_scale;
         a.attn = attn; a.heads = heads; a.x = x; a.x1 = x1; a.p1 = p_attn_out; a.seed1 = seed_attn_out; a.sign = res_sign;
         a.B = B; a.n = n; a.p = pos_dim; a.tiles = tiles;
-        enc_attn_kernel<<<B * tiles, THREADS, ATT_SMEM, st>>>(mq, a);
+        launch_enc(enc_attn_kernel, B * tiles, ATT_SMEM, st, mq, a);
         ++launched;
     }
     if (stages & 4) {
@@ -865,7 +868,7 @@ extern "C" int gb200_encoder_layer_fwd(int device, const void* packed, int d_mod
         a.w1tiles = wt + (size_t)TS_W1 * TILE_BYTES; a.w2tiles = wt + (size_t)TS_W2 * TILE_BYTES; a.vec = vec; a.x1 = x1;
         a.hbuf = hidden; a.x2 = x2; a.pf = p_ffn; a.p2 = p_out; a.rscale = 1.f; a.seedf = seed_ffn; a.seed2 = seed_out;
         a.seed_off = rng_offset_ptr(); a.B = B; a.n = n; a.tiles = tiles;
-        enc_ffn_kernel<<<B * tiles, THREADS, FFN_SMEM, st>>>(m1, a);
+        launch_enc(enc_ffn_kernel, B * tiles, FFN_SMEM, st, m1, a);
         ++launched;
     }
     return check_launch("gb200_encoder_layer_fwd", launched);

@@ -167,8 +167,8 @@ __device__ __forceinline__ void tc_epilogue_vec4(const TcArgs& g, const float* _
 }
 
 template <int BN, bool A_MN, bool B_MN, bool SPLIT = false>
-__global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                             const __grid_constant__ CUtensorMap mapB, TcArgs g) {
+__device__ __forceinline__ void gemm_tc_body(const CUtensorMap& mapA, const CUtensorMap& mapB, const TcArgs& g, int bx, int by,
+                                             int bz) {
     constexpr int A_BYTES = TC_BM * TC_BK * 4;          // 16 KB
     constexpr int B_BYTES = BN * TC_BK * 4;
     constexpr int TILE_PAIR = A_BYTES + B_BYTES;        // what TMA lands per k-block
@@ -184,8 +184,8 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
-    const int split = blockIdx.z;
+    const int m0 = by * TC_BM, n0 = bx * BN;
+    const int split = bz;
     const int kbeg = split * g.kchunk;
     const int kend = min(g.K, kbeg + g.kchunk);
     const int nkb = (kend - kbeg + TC_BK - 1) / TC_BK;
@@ -441,6 +441,43 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(tc_tmem_cols<BN>())
                      : "memory");
+    }
+}
+
+template <int BN, bool A_MN, bool B_MN, bool SPLIT = false>
+__global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                             const __grid_constant__ CUtensorMap mapB, TcArgs g) {
+    gemm_tc_body<BN, A_MN, B_MN, SPLIT>(mapA, mapB, g, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// Grouped launch: up to TC_GROUP_MAX independent split-K problems (the weight gradients of one encoder layer) in ONE grid,
+// so their CTAs fill the GPU together instead of queueing behind one another on side streams.
+constexpr int TC_GROUP_MAX = 6;
+struct TcGroup {
+    CUtensorMap mapA[TC_GROUP_MAX], mapB[TC_GROUP_MAX];
+    TcArgs g[TC_GROUP_MAX];
+    int first[TC_GROUP_MAX + 1];      // CTA index range of each problem
+    int tn[TC_GROUP_MAX], tm[TC_GROUP_MAX];
+    int n;
+};
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS) gemm_tc_group_kernel(const __grid_constant__ TcGroup G) {
+    int p = 0;
+    while (p + 1 < G.n && (int)blockIdx.x >= G.first[p + 1]) ++p;
+    const int local = blockIdx.x - G.first[p];
+    const int bx = local % G.tn[p], by = (local / G.tn[p]) % G.tm[p], bz = local / (G.tn[p] * G.tm[p]);
+    gemm_tc_body<BN, true, true, false>(G.mapA[p], G.mapB[p], G.g[p], bx, by, bz);
+}
+__global__ void tc_splitk_reduce_group_kernel(const __grid_constant__ TcGroup G) {
+    const TcArgs& g = G.g[blockIdx.y];
+    if (g.ksplit <= 1) return;          // that problem's CTAs wrote the final values themselves
+    const long long total = (long long)g.M * g.N;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(e % g.N);
+        const int m = (int)(e / g.N);
+        float s = 0.f;
+        for (int k = 0; k < g.ksplit; ++k) s += g.ws[(long long)k * total + e];
+        g.ep.C[(long long)m * g.ep.ldc + n] = s;
     }
 }
 
@@ -889,6 +926,67 @@ extern "C" int gb200_gemm_tc_gated(int device, const float* A, int lda, int tran
                                  0, drop_p, seed, nullptr, 0, rscale, 0, ksplit, workspace, workspace_bytes, stream);
     gg.G = nullptr;
     return rc;
+}
+
+extern "C" size_t gb200_gemm_tc_wgrad_group_workspace_bytes(int n, const gb200_wgrad_problem* probs) {
+    size_t total = 0;
+    for (int i = 0; i < n; ++i) total += (size_t)64 * probs[i].M * probs[i].N * sizeof(float);   // upper bound: ksplit <= 64
+    return total;
+}
+
+/* dW_i (M_i, N_i) = G_i^T X_i for i < n <= 4: the weight gradients of one layer (contractions over all T tokens) as ONE
+ * tcgen05 TF32 split-K launch plus ONE fixed-order reduction (deterministic). */
+extern "C" int gb200_gemm_tc_wgrad_group(int device, int n, const gb200_wgrad_problem* probs, float* workspace,
+                                         size_t workspace_bytes, void* stream) {
+    use_device(device);
+    GB_REQUIRE(n >= 1 && n <= TC_GROUP_MAX && probs && workspace, "gb200_gemm_tc_wgrad_group: 1..%d problems", TC_GROUP_MAX);
+    TcGroup G;
+    memset(&G, 0, sizeof(G));
+    G.n = n;
+    int tiles = 0;
+    for (int i = 0; i < n; ++i) {
+        const gb200_wgrad_problem& q = probs[i];
+        GB_REQUIRE(q.G && q.X && q.dW && q.T >= 1, "gb200_gemm_tc_wgrad_group: null operand in problem %d", i);
+        GB_REQUIRE(gb200_gemm_tc_supported(q.G, q.ldg, q.X, q.ldx, q.M, q.N, (int)q.T) && q.N % 4 == 0 && q.ldw % 4 == 0 &&
+                       ((uintptr_t)q.dW % 16) == 0,
+                   "gb200_gemm_tc_wgrad_group: problem %d is not TMA / float4 aligned", i);
+        tiles += cdiv(q.M, TC_BM) * cdiv(q.N, 128);
+    }
+    int S = (2 * 148) / tiles;
+    if (S < 1) S = 1;
+    if (S > 64) S = 64;
+    size_t woff = 0;
+    int cta = 0;
+    const CUtensorMapSwizzle SWMN = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    for (int i = 0; i < n; ++i) {
+        const gb200_wgrad_problem& q = probs[i];
+        TcArgs& g = G.g[i];
+        const int K = (int)q.T;
+        g.ep.C = q.dW; g.ep.ldc = q.ldw; g.ep.alpha = 1.f; g.ep.rscale = 1.f; g.ep.act = ACT_NONE;
+        g.M = q.M; g.N = q.N; g.K = K;
+        g.kchunk = cdiv(cdiv(K, TC_BK), S) * TC_BK;
+        g.ksplit = cdiv(K, g.kchunk);
+        g.ws = workspace + woff;
+        g.vec4 = 1;
+        woff += (size_t)g.ksplit * q.M * q.N;
+        GB_REQUIRE(make_map(&G.mapA[i], q.G, q.M, K, q.ldg, 32, 32, SWMN) && make_map(&G.mapB[i], q.X, q.N, K, q.ldx, 32, 32, SWMN),
+                   "gb200_gemm_tc_wgrad_group: cuTensorMapEncodeTiled failed (problem %d)", i);
+        G.tn[i] = cdiv(q.N, 128);
+        G.tm[i] = cdiv(q.M, TC_BM);
+        G.first[i] = cta;
+        cta += G.tn[i] * G.tm[i] * g.ksplit;
+    }
+    G.first[n] = cta;
+    GB_REQUIRE(workspace_bytes >= woff * sizeof(float), "gb200_gemm_tc_wgrad_group: workspace too small");
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(gemm_tc_group_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<128>());
+        configured = true;
+    }
+    cudaStream_t st = as_stream(stream);
+    gemm_tc_group_kernel<128><<<cta, TC_THREADS, tc_smem_bytes<128>(), st>>>(G);
+    tc_splitk_reduce_group_kernel<<<dim3(64, n), 256, 0, st>>>(G);
+    return check_launch("gb200_gemm_tc_wgrad_group", 2);
 }
 
 /* y = x W^T + b with per-head LayerNorm statistics fused into the epilogue: columns [col_lo, col_hi) of the output

@@ -260,6 +260,24 @@ def gemm(A, B, C, M, N, K, *, lda, ldb, ldc, transA=False, transB=False, alpha=1
             drop_p, seed, ptr(residual), ldr, rscale, int(accumulate), ksplit, ptr(ws), ws_bytes, stream_of(C))
 
 
+def wgrad_group(problems, T):
+    """[(G (T, M) view, M, ldg, X (T, N), N, dW (M, N)), ...] (at most 6): dW = G^T X for each, one tcgen05 TF32 split-K launch
+    and one deterministic reduction for the whole group (gb200_gemm_tc_wgrad_group)."""
+    lib = _lib.load()
+    n = len(problems)
+    arr = (_lib.WgradProblem * n)()
+    flops = nbytes = 0.0
+    for i, (G_, M, ldg, X_, N, dW) in enumerate(problems):
+        arr[i].G, arr[i].ldg, arr[i].X, arr[i].ldx = G_.data_ptr(), ldg, ptr(X_), N
+        arr[i].dW, arr[i].ldw, arr[i].M, arr[i].N, arr[i].T = ptr(dW), N, M, N, T
+        flops += 2.0 * T * M * N
+        nbytes += 4.0 * (T * (M + N) + M * N)
+    like = problems[0][0]
+    wsb = lib.gb200_gemm_tc_wgrad_group_workspace_bytes(n, arr)
+    ws = workspace(wsb, like)
+    _launch("gemm_tc_tn", flops, nbytes, lib.gb200_gemm_tc_wgrad_group, _dev(like), n, arr, ptr(ws), wsb, stream_of(like))
+
+
 def colsum(X, M, N, ld, out, *, x_off=0, scale=1.0, accumulate=False):
     lib = _lib.load()
     ws_bytes = lib.gb200_colsum_workspace_bytes(M, N)
@@ -938,10 +956,11 @@ def linear_attention(query, key, value, pos, flat, has_norm, keep_mask, *, n_hea
 # Fused encoder layer (csrc/encoder_fwd.cu): three tcgen05 kernels per layer forward
 # ------------------------------------------------------------------------------------------
 _FUSED_BACKWARD = os.environ.get("GB200_FUSED_BACKWARD", "1") != "0"     # A/B switch: 0 = per-operator backward
-# 1 = the launching stream joins the weight-gradient side streams only when the whole backward pass is enqueued.  Measured
-# at C3: 7.28 vs 7.33 ms/step -- the GEMMs are not dependency- but SM-bound (a fused-kernel CTA owns its SM's shared
-# memory), and the late join is unsafe with concurrent micro-batch chains, so it stays opt-in.
-_DEFER_WGRAD_JOIN = os.environ.get("GB200_DEFER_WGRAD_JOIN", "0") == "1"
+# The launching stream joins the weight-gradient side stream only when the whole backward pass is enqueued (autograd engine
+# callback), so the grouped weight-gradient GEMM of layer l overlaps the input-gradient chain of layers l-1, l-2, ...
+# Measured at C3 with the grouped launch: 4.82 -> 4.67 ms/step.  GB200_DEFER_WGRAD_JOIN=0 joins per layer (graphs.GraphedStep does
+# that itself for concurrent micro-batch chains, whose per-chain streams are joined before the backward pass ends).
+_DEFER_WGRAD_JOIN = os.environ.get("GB200_DEFER_WGRAD_JOIN", "1") != "0"
 
 
 class _Ctx:
@@ -1085,8 +1104,10 @@ class _EncoderLayerFn(torch.autograd.Function):
         dqkv = torch.empty((T, 3 * dm), **f32)
         dx = torch.empty((B, n, dm), **f32)
         dvec = torch.empty(3 * dm + 4 * dm + dm + dff + dm, **f32)
+        # every weight gradient is its own tensor: autograd then adopts it as .grad without a copy kernel (a view, or a tensor
+        # somebody else still references, would be cloned on the launching stream before the side-stream GEMM has written it)
         dw2, dw1, dwfc = torch.empty_like(params[-2]), torch.empty_like(params[-4]), torch.empty_like(params[-6])
-        dwqkv = torch.empty((3 * dm, dm), **f32)
+        dwq, dwk, dwv = (torch.empty((dm, dm), **f32) for _ in range(3))
         wsb = lib.gb200_encoder_bwd_workspace_bytes(B, n, H, dk, p)
         ws = workspace(wsb, x)
 
@@ -1098,24 +1119,22 @@ class _EncoderLayerFn(torch.autograd.Function):
 
         fork = _Fork(dy2)
         stage(1, 4.0 * T * dm * dff, 4.0 * T * (3 * dm + 2 * dff))
-        with fork.side(0):
-            gemm(g2 if g2 is not None else dy2, hid, dw2, dm, dff, T, lda=dm, ldb=dff, ldc=dff, transA=True, wgrad=True)
-        with fork.side(1):
-            gemm(g1, x1, dw1, dff, dm, T, lda=dff, ldb=dm, ldc=dm, transA=True, wgrad=True)
         stage(2, 2.0 * T * H * d * dm + 8.0 * B * H * n * d * d, 4.0 * T * (4 * dm))
-        with fork.side(2):
-            gemm(gfc if gfc is not None else dx1, heads.reshape(T, H * d), dwfc, dm, H * d, T, lda=dm, ldb=H * d, ldc=H * d,
-                 transA=True, wgrad=True)
         stage(4, 8.0 * B * H * n * d * d, 4.0 * T * (4 * dm))
         stage(8, 2.0 * T * 3 * dm * dm, 4.0 * T * (5 * dm))
-        with fork.side(3):
-            gemm(dqkv, x.reshape(T, dm), dwqkv, 3 * dm, dm, T, lda=3 * dm, ldb=dm, ldc=dm, transA=True, wgrad=True)
+        with fork.side(0):      # the four weight gradients of the layer: one grouped split-K launch + one reduction
+            x2d = x.reshape(T, dm)
+            wgrad_group([(g2 if g2 is not None else dy2, dm, dm, hid, dff, dw2),
+                         (g1, dff, dff, x1, dm, dw1),
+                         (gfc if gfc is not None else dx1, dm, dm, heads.reshape(T, H * d), H * d, dwfc),
+                         (dqkv, dm, 3 * dm, x2d, dm, dwq), (dqkv[:, dm:], dm, 3 * dm, x2d, dm, dwk),
+                         (dqkv[:, 2 * dm:], dm, 3 * dm, x2d, dm, dwv)], T)
         stage(16, 0.0, 0.0)
         if _DEFER_WGRAD_JOIN:
-            fork.join_at_end_of_backward((dy2, g2, g1, dx1, gfc, dqkv, hid, x1, heads, x, dw2, dw1, dwfc, dwqkv))
+            fork.join_at_end_of_backward((dy2, g2, g1, dx1, gfc, dqkv, hid, x1, heads, x))
         else:
             fork.join()
-        grads = [dwqkv[i * dm:(i + 1) * dm] for i in range(3)] + [dvec[i * dm:(i + 1) * dm] for i in range(3)]
+        grads = [dwq, dwk, dwv] + [dvec[i * dm:(i + 1) * dm] for i in range(3)]
         o = 3 * dm
         if has_norm:
             grads += [dvec[o + i * dk:o + (i + 1) * dk] for i in range(4 * H)]

@@ -34,6 +34,8 @@ class GraphedStep:
         self.static_inputs = [t.clone() for t in example_inputs]
         self.step_fn = step_fn
         self.batch_streams = int(batch_streams)
+        if self.batch_streams > 1:       # per-chain streams: weight-gradient side streams must be joined inside each chain
+            GF._DEFER_WGRAD_JOIN = False
         if self.batch_streams > 1:
             for t in self.static_inputs:
                 assert t.shape[0] % self.batch_streams == 0, "batch must divide evenly over batch_streams"

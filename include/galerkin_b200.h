@@ -87,6 +87,19 @@ int gb200_gemm_tc(int device, const float* A, int lda, int transA, const float* 
                   float rscale, int accumulate, int ksplit, float* workspace, size_t workspace_bytes,
                   void* stream);
 
+/* Grouped weight gradients: dW_i (M_i, N_i) = G_i^T X_i, i < n <= 6, each a contraction over all T_i rows (tokens), as ONE
+ * tcgen05 TF32 split-K grid plus ONE fixed-order reduction -- the four weight gradients of an encoder layer
+ * (libs/layers.py:837-839, :896-897, :980-986 in backward) fill the GPU together instead of queueing as eight launches. */
+typedef struct gb200_wgrad_problem {
+    const float* G; int ldg;        /* (T, M) gradient w.r.t. the layer output */
+    const float* X; int ldx;        /* (T, N) layer input */
+    float* dW; int ldw;             /* (M, N) */
+    int M, N; long long T;
+} gb200_wgrad_problem;
+size_t gb200_gemm_tc_wgrad_group_workspace_bytes(int n, const gb200_wgrad_problem* probs);
+int gb200_gemm_tc_wgrad_group(int device, int n, const gb200_wgrad_problem* probs, float* workspace, size_t workspace_bytes,
+                              void* stream);
+
 /* Gated GEMM: C = rscale * dropout_p( (alpha * op(A).op(B)) * act'(gate) ), gate_act = GB200_ACT_RELU (keep where
  * gate > 0; `gate` may be the stored post-activation/post-dropout output) or GB200_ACT_SILU (times silu'(gate), `gate`
  * = stored pre-activation).  With (seed, drop_p, rscale) of the forward layer this is "input gradient of layer i+1,
