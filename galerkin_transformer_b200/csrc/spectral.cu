@@ -57,15 +57,20 @@ __global__ void __launch_bounds__(128) ydft_kernel(const float* __restrict__ x, 
         }
         __syncthreads();
         if (active) {
+            // sixteen independent loads in flight per thread (the grid is only ~8 warps per SM: latency, not bandwidth, binds)
             const float* xp = x + (R * n + y0) * C + c;
-#pragma unroll 2
-            for (int yy = 0; yy < ny; ++yy) {
-                const float v = xp[(long long)yy * C];
+            for (int yb = 0; yb < ny; yb += 16) {
+                float v[16];
 #pragma unroll
-                for (int k = 0; k < KYG; ++k) {
-                    const float2 t = tws[k][yy];
-                    are[k] = fmaf(v, t.x, are[k]);
-                    aim[k] = fmaf(-v, t.y, aim[k]);
+                for (int j = 0; j < 16; ++j) v[j] = (yb + j < ny) ? xp[(long long)(yb + j) * C] : 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+#pragma unroll
+                    for (int k = 0; k < KYG; ++k) {
+                        const float2 t = tws[k][yb + j];
+                        are[k] = fmaf(v[j], t.x, are[k]);
+                        aim[k] = fmaf(-v[j], t.y, aim[k]);
+                    }
                 }
             }
         }
@@ -140,11 +145,19 @@ __global__ void xidft_kernel(const float2* __restrict__ Oft, int B, int n, int m
     const float2* op = Oft + (((long long)b * 2 * m) * m + ky) * C + c;
     const long long rstride = (long long)m * C;
     float zre = 0.f, zim = 0.f;
-    for (int r = 0; r < 2 * m; ++r) {
-        const float2 o = op[r * rstride];
-        const float2 w = __ldg(twX + (long long)r * n + X);
-        zre = fmaf(o.x, w.x, fmaf(-o.y, w.y, zre));
-        zim = fmaf(o.x, w.y, fmaf(o.y, w.x, zim));
+    for (int r0 = 0; r0 < 2 * m; r0 += 8) {
+        float2 o[8], w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool ok = r0 + j < 2 * m;
+            o[j] = ok ? op[(r0 + j) * rstride] : make_float2(0.f, 0.f);
+            w[j] = ok ? __ldg(twX + (long long)(r0 + j) * n + X) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            zre = fmaf(o[j].x, w[j].x, fmaf(-o[j].y, w[j].y, zre));
+            zim = fmaf(o[j].x, w[j].y, fmaf(o[j].y, w[j].x, zim));
+        }
     }
     Z[e] = make_float2(zre * scale, zim * scale);
 }
@@ -219,14 +232,24 @@ __global__ void mix_bwd_w_kernel(const float2* __restrict__ Xf, const float2* __
     const int o = blockIdx.y, half = blockIdx.z;
     if (mode >= M2) return;
     float2* dW = half == 0 ? dW0 : dW1;
+    // batch entries in groups of 8: their dO values are loaded once, and for every input channel the 8 X^ loads are issued
+    // together (the grid is small -- a few hundred warps -- so loads in flight per thread are what hides the latency)
     for (int i = 0; i < Ci; ++i) {
         float are = 0.f, aim = 0.f;
-        for (int b = 0; b < B; ++b) {
-            const long long q = ((long long)b * halves + half) * M2 + mode;
-            const float2 x = Xf[q * Ci + i];
-            const float2 g = dO[q * Co + o];
-            are = fmaf(x.x, g.x, fmaf(x.y, g.y, are));
-            aim = fmaf(x.x, g.y, fmaf(-x.y, g.x, aim));
+        for (int b0 = 0; b0 < B; b0 += 8) {
+            float2 x[8], g[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const bool ok = b0 + j < B;
+                const long long q = ((long long)(ok ? b0 + j : b0) * halves + half) * M2 + mode;
+                x[j] = ok ? Xf[q * Ci + i] : make_float2(0.f, 0.f);
+                g[j] = ok ? dO[q * Co + o] : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                are = fmaf(x[j].x, g[j].x, fmaf(x[j].y, g[j].y, are));
+                aim = fmaf(x[j].x, g[j].y, fmaf(-x[j].y, g[j].x, aim));
+            }
         }
         float2* dst = dW + ((long long)i * Co + o) * M2 + mode;
         if (accumulate) { float2 old = *dst; are += old.x; aim += old.y; }

@@ -6,7 +6,7 @@ tag=${1:-r02z}
 python bench.py --steps 20 --warmup 5 2>gpurun_out/${tag}_bench.err | tail -1 > gpurun_out/${tag}_bench.json
 ncu --metrics gpu__time_duration.sum --clock-control none -s 1200 -c 1400 --csv --log-file gpurun_out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph --no-parts > gpurun_out/${tag}_launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'enc_|conv3x3_tc|conv_split|gemm_tc_kernel' -s 17 -c 19 -f \
+ncu --set full --clock-control none --import-source on -k regex:'enc_|conv3x3_tc|conv_split|gemm_tc' -s 10 -c 14 -f \
     -o gpurun_out/${tag}_fused python tools/run_layer_once.py > gpurun_out/${tag}_fused.log 2>&1
 ncu -i gpurun_out/${tag}_fused.ncu-rep --page raw --csv > gpurun_out/${tag}_fused.raw.csv 2>/dev/null
 python tools/trace_fused.py --warm > gpurun_out/${tag}_trace_fwd.txt 2>&1
