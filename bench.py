@@ -311,11 +311,19 @@ def merge_gemm_layouts(summary):
 
 
 def ncu_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the CURRENT
+    build (profiles/ncu_traffic.json is rewritten by tools/ncu_summary.py from every tools/final_profile.sh run)."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(path):
         with open(path) as f:
-            return json.load(f).get(kernel)
+            table = json.load(f)
+        for key, v in table.items():
+            if key.split("::")[-1].replace("_kernel", "").replace("void ", "").split("<")[0] in (kernel, kernel + "_kernel"):
+                return v
+        stem = kernel.replace("_kernel", "")
+        for key, v in table.items():
+            if stem in key:
+                return v
     return None
 
 

@@ -1030,12 +1030,19 @@ class _EncoderLayerFn(torch.autograd.Function):
         x2 = torch.empty((B, n, dm), **f32)
         wsb = lib.gb200_encoder_workspace_bytes(B, n, H, dk, p)
         ws = workspace(wsb, x)
-        gflop = 2.0 * T * (3 * dm * dm + H * d * dm + 2 * dm * dff) + 4.0 * B * H * n * d * d
-        nbytes = 4.0 * T * (2 * dm + 3 * dm + H * d + dm + dff) + 2.0 * packed.numel()
-        _launch("encoder_layer_fwd", gflop, nbytes, lib.gb200_encoder_layer_fwd, dev, ptr(packed), dm, H, p, dff, ptr(x),
-                ptr(pos), B, n, int(has_norm), eps, scale, ptr(keep_mask), mask_p, mask_seed, p1, seed1, sign, pf, seedf,
-                p2, seed2, ptr(qkv), ptr(rstd[0]), ptr(rstd[1]), ptr(A), ptr(heads), ptr(x1), ptr(hid), ptr(x2), ptr(ws),
-                wsb, 7, st)
+        # ALGORITHMIC work per kernel: flops of the GEMMs it carries, bytes of the tensors it must read / write
+        work = {1: ("enc_qkv", 2.0 * T * 3 * dm * dm + 2.0 * B * H * n * d * d, 4.0 * T * (dm + 3 * dm + 2 * H) + 2.0 * 3 * dm * dm),
+                2: ("enc_attn", 2.0 * B * H * n * d * d + 2.0 * T * H * d * dm, 4.0 * T * (dm + H * d + 2 * dm) + 2.0 * H * d * dm),
+                4: ("enc_ffn", 4.0 * T * dm * dff, 4.0 * T * (dm + dff + dm) + 4.0 * dm * dff)}
+        args = (dev, ptr(packed), dm, H, p, dff, ptr(x), ptr(pos), B, n, int(has_norm), eps, scale, ptr(keep_mask), mask_p,
+                mask_seed, p1, seed1, sign, pf, seedf, p2, seed2, ptr(qkv), ptr(rstd[0]), ptr(rstd[1]), ptr(A), ptr(heads),
+                ptr(x1), ptr(hid), ptr(x2), ptr(ws), wsb)
+        if Profiler.enabled:       # attribution pass: one launch per event pair
+            for bit, (fam, fl, by) in work.items():
+                _launch(fam, fl, by, lib.gb200_encoder_layer_fwd, *args, bit, st)
+        else:
+            _launch("encoder_layer_fwd", sum(w[1] for w in work.values()), sum(w[2] for w in work.values()),
+                    lib.gb200_encoder_layer_fwd, *args, 7, st)
         ctx.save_for_backward(x, pos, keep_mask, qkv, A, heads, x1, hid, packed, *[r for r in rstd if r is not None],
                               *params)
         ctx.cfg = cfg
@@ -1111,17 +1118,19 @@ class _EncoderLayerFn(torch.autograd.Function):
         wsb = lib.gb200_encoder_bwd_workspace_bytes(B, n, H, dk, p)
         ws = workspace(wsb, x)
 
+        names = {1: "enc_ffn_bwd", 2: "enc_attn_bwd", 4: "enc_kv_bwd", 8: "enc_dx", 16: "enc_reduce"}
+
         def stage(bits, flops, nbytes):
-            _launch("encoder_layer_bwd", flops, nbytes, lib.gb200_encoder_layer_bwd, dev, ptr(packed), dm, H, p, dff, ptr(dy2),
+            _launch(names[bits], flops, nbytes, lib.gb200_encoder_layer_bwd, dev, ptr(packed), dm, H, p, dff, ptr(dy2),
                     ptr(pos), B, n, int(has_norm), scale, ptr(keep_mask), mask_p, mask_seed, p1, seed1, sign, pf, p2, seed2,
                     ptr(qkv), ptr(rstd[0]) if has_norm else None, ptr(rstd[1]) if has_norm else None, ptr(A), ptr(hid),
                     ptr(g2), ptr(g1), ptr(dx1), ptr(gfc), ptr(dqkv), ptr(dx), ptr(dvec), ptr(ws), wsb, bits, st)
 
         fork = _Fork(dy2)
-        stage(1, 4.0 * T * dm * dff, 4.0 * T * (3 * dm + 2 * dff))
-        stage(2, 2.0 * T * H * d * dm + 8.0 * B * H * n * d * d, 4.0 * T * (4 * dm))
-        stage(4, 8.0 * B * H * n * d * d, 4.0 * T * (4 * dm))
-        stage(8, 2.0 * T * 3 * dm * dm, 4.0 * T * (5 * dm))
+        stage(1, 4.0 * T * dm * dff, 4.0 * T * (dm + dff + dff + dm) + 4.0 * dm * dff)                 # dy, hid -> g1, dx1
+        stage(2, 2.0 * T * H * d * dm + 4.0 * B * H * n * d * d, 4.0 * T * (dm + dm + dm) + 2.0 * H * d * dm)    # dx1, Q -> dQ (+G)
+        stage(4, 4.0 * B * H * n * d * d, 4.0 * T * (2 * dm + 2 * dm + 2 * H))                         # x^K, x^V -> dK, dV
+        stage(8, 2.0 * T * 3 * dm * dm, 4.0 * T * (3 * dm + dm + dm) + 2.0 * 3 * dm * dm)              # dqkv, dx1 -> dx
         with fork.side(0):      # the four weight gradients of the layer: one grouped split-K launch + one reduction
             x2d = x.reshape(T, dm)
             wgrad_group([(g2 if g2 is not None else dy2, dm, dm, hid, dff, dw2),
