@@ -36,10 +36,11 @@ void set_error(const char* fmt, ...) {
 }
 
 void use_device(int device) {
-    if (device >= 0 && device != g_device) {
-        cudaSetDevice(device);
-        g_device = device;
-    }
+    // the caller (PyTorch) may have switched this thread's current device since the last call: ask, do not cache
+    if (device < 0) return;
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != device) cudaSetDevice(device);
+    g_device = device;
 }
 
 int check_launch(const char* what, int nkernels) {

@@ -54,13 +54,22 @@ _seed_lock = threading.Lock()
 _seed_counter = 0
 
 
+def _rank():
+    try:
+        import torch.distributed as dist
+        return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    except Exception:
+        return 0
+
+
 def next_seed():
-    """64-bit Philox key for one fused-dropout site: derived from torch's seed and a call counter
-    (deterministic under torch.manual_seed, distinct per call and per rank)."""
+    """63-bit Philox key for one fused-dropout site: derived from torch's seed, the distributed rank (identically seeded
+    data-parallel replicas still draw different masks on their shards) and a process-local call counter -- deterministic
+    under torch.manual_seed."""
     global _seed_counter
     with _seed_lock:
         _seed_counter += 1
-        c = _seed_counter
+        c = _seed_counter + 0x51ED270B * _rank()
     # 63 bits: the value travels through autograd.Function arguments, which profilers convert to int64
     return (torch.initial_seed() * 0x9E3779B97F4A7C15 + c * 0xD1B54A32D192ED03) & 0x7FFFFFFFFFFFFFFF
 
@@ -85,6 +94,18 @@ def rng_step_counter(device=None):
 
 def advance_rng():
     rng_step_counter().add_(0x9E3779B1)
+
+
+def get_rng_state():
+    """(call counter, device step counter) of the fused-dropout streams -- put it in checkpoints next to torch's RNG state"""
+    return dict(seed_counter=_seed_counter, step=int(rng_step_counter().item()) if _rng_step is not None else None)
+
+
+def set_rng_state(state):
+    global _seed_counter
+    _seed_counter = int(state["seed_counter"])
+    if state.get("step") is not None:
+        rng_step_counter().fill_(int(state["step"]))
 
 
 class Profiler:
@@ -344,8 +365,9 @@ class _LinearFn(torch.autograd.Function):
         y = torch.empty((M, N), dtype=torch.float32, device=x.device)
         # backward needs act'(z): SiLU always from z; ReLU from the stored output unless a residual
         # was folded into it
-        need_z = (act == ACT["silu"] or (act == ACT["relu"] and residual is not None)) \
-            and (x.requires_grad or weight.requires_grad)
+        # (a ReLU gate read from the stored output y = rscale * drop(relu(z)) needs rscale > 0)
+        needs_grad = x.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad)
+        need_z = (act == ACT["silu"] or (act == ACT["relu"] and (residual is not None or rscale <= 0.0))) and needs_grad
         z = torch.empty_like(y) if need_z else None
         gemm(x, weight, y, M, N, K, lda=K, ldb=K, ldc=N, transB=True, bias=bias, act=act, zout=z, ldz=N,
              drop_p=drop_p, seed=seed, residual=residual, ldr=N, rscale=rscale)
@@ -409,7 +431,8 @@ class _MLP2Fn(torch.autograd.Function):
         M, K = x.shape
         N1, N2 = w1.shape[0], w2.shape[0]
         h = torch.empty((M, N1), dtype=torch.float32, device=x.device)
-        need_grad = x.requires_grad or w1.requires_grad or w2.requires_grad
+        need_grad = x.requires_grad or w1.requires_grad or w2.requires_grad or \
+            (b1 is not None and b1.requires_grad) or (b2 is not None and b2.requires_grad)
         z1 = torch.empty_like(h) if (act == ACT["silu"] and need_grad) else None
         gemm(x, w1, h, M, N1, K, lda=K, ldb=K, ldc=N1, transB=True, bias=b1, act=act, zout=z1, ldz=N1, drop_p=p1,
              seed=seed1)

@@ -147,6 +147,11 @@ class SimpleAttention(nn.Module):
         # Fourier type: without a dropout between the two products (QK^T)V = Q(K^T V) exactly, so the O(n d^2)
         # linear-form kernels are used; with the n x n dropout the quadratic flash-style kernels run instead.
         quadratic = fourier and (keep is not None or mask_p > 0.0 or self.materialize_attn)
+        if quadratic and d > 64:
+            raise NotImplementedError(
+                f"Fourier-type attention with the n x n dropout (attn_dropout='reference'), a keep-mask or materialize_attn "
+                f"runs the quadratic flash-style kernels, which support d_k + pos_dim <= 64 (got {d}); "
+                "set_attn_dropout(model, 'off') selects the exact linear-form kernels (d_k + pos_dim <= 128)")
 
         x, attn = GF.linear_attention(query, key, value, pos if use_pos else None, flat, bool(self.add_norm),
                                       keep, n_head=self.n_head, pos_dim=p,

@@ -421,6 +421,37 @@ class _ConfiguredModel(nn.Module):
                   'num_regressor_layers', 'fourier_modes', 'dropout', 'downscaler_dropout',
                   'upscaler_dropout', 'upsample_mode', 'downsample_mode', 'last_activation', 'debug']
 
+    # the reference moves its (non-Module) normalizer together with the model: libs/model.py:1026-1042
+    def _move_normalizer(self, fn):
+        for owner in (self, getattr(self, "regressor", None)):
+            norm = getattr(owner, "normalizer", None) if owner is not None else None
+            if norm is not None and hasattr(norm, fn):
+                moved = getattr(norm, fn)()
+                if moved is not None:
+                    owner.normalizer = moved
+
+    def cuda(self, device=None):
+        out = super().cuda(device)
+        self._move_normalizer("cuda")
+        return out
+
+    def cpu(self):
+        out = super().cpu()
+        self._move_normalizer("cpu")
+        return out
+
+    def to(self, *args, **kwargs):
+        out = super().to(*args, **kwargs)
+        dev = next((a for a in args if isinstance(a, (str, torch.device))), kwargs.get("device"))
+        if dev is not None:
+            for owner in (self, getattr(self, "regressor", None)):
+                norm = getattr(owner, "normalizer", None) if owner is not None else None
+                if norm is not None and hasattr(norm, "to"):
+                    moved = norm.to(dev)
+                    if moved is not None:
+                        owner.normalizer = moved
+        return out
+
     def _absorb(self, kwargs):
         self.config = defaultdict(lambda: None, **kwargs)
         for key in list(self.config.keys()) + ADDITIONAL_ATTR + self.KNOWN_KEYS:

@@ -448,3 +448,31 @@ def test_gemm_split_tf32_is_fp32_grade(M, N, K, tA, tB):
     GF.gemm(A, B, Cw, M, N, K, lda=A.shape[1], ldb=B.shape[1], ldc=N, transA=tA, transB=tB, wgrad=True)   # single-pass TF32
     plain = (A.double().t() if tA else A.double()) @ (B.double().t() if tB else B.double())
     assert rel_l2(Cw, plain) < 2e-3, rel_l2(Cw, plain)      # (unaligned leading dimensions fall back to the exact kernel)
+
+
+def test_fourier_quadratic_width_limit_is_a_clean_error():
+    """reference ex1_burgers config (attention_type fourier, n_hidden 96, 1 head, pos_dim 1 -> d = 97): the always-on n x n
+    dropout needs the quadratic kernels (d <= 64) -> NotImplementedError with a hint; 'off' runs the exact linear form."""
+    import galerkin_transformer_b200 as G
+    a = G.SimpleAttention(n_head=1, d_model=96, pos_dim=1, attention_type="fourier", norm=True).to(DEV)
+    x, pos = rn(2, 64, 96), torch.rand(2, 64, 1, device=DEV)
+    with pytest.raises(NotImplementedError, match="set_attn_dropout"):
+        a(x, x, x, pos=pos)
+    G.set_attn_dropout(a, "off")
+    out, _ = a(x, x, x, pos=pos)
+    assert out.shape == (2, 64, 96) and torch.isfinite(out).all()
+
+
+def test_linear_relu_negative_rscale_and_bias_only_grads():
+    """a ReLU gate must not be read from an output scaled by rscale <= 0; bias-only gradients need z for SiLU"""
+    x, W, b = rn(40, 24), rn(16, 24, seed=1).requires_grad_(True), rn(16, seed=2).requires_grad_(True)
+    y = GF.linear(x, W, b, act="relu", rscale=-1.0)
+    y.sum().backward()
+    ref_gate = ((x.double() @ W.detach().double().t() + b.detach().double()) > 0).double()
+    assert rel_l2(b.grad, -ref_gate.sum(0)) < 1e-6
+    b2 = rn(16, seed=3).requires_grad_(True)
+    y2 = GF.linear(x, W.detach(), b2, act="silu")
+    y2.sum().backward()
+    z = x.double() @ W.detach().double().t() + b2.detach().double()
+    sg = torch.sigmoid(z)
+    assert rel_l2(b2.grad, (sg * (1 + z * (1 - sg))).sum(0)) < 1e-5
