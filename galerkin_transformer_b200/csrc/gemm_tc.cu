@@ -33,6 +33,12 @@ constexpr int TC_BM = 128, TC_BK = 32, TC_THREADS = 192;
 // one-CTA-per-SM ring for the long-K weight-gradient GEMMs was measured and is slower (tools/bench_gemm.py)
 // (6 for MN/MN measured slower).  Narrow tiles (BN <= 64, 24 KB stages) afford a 4th stage at the same occupancy;
 // the 192-wide tile (N = 384 in one wave of 232 CTAs instead of 348 in two) has room for two.
+// split (3xTF32) stages are twice as large: two of them keep the CTA under half an SM's shared memory for BN <= 64, so two
+// CTAs co-reside and one's prologue / epilogue overlaps the other's main loop (the tall-skinny decoder GEMMs are 8 waves of
+// single-tile CTAs: with one CTA per SM those phases were serialised, 62 us for a 16 us problem)
+#ifndef GB200_TC_STAGES_SPLIT
+#define GB200_TC_STAGES_SPLIT 2
+#endif
 #ifndef GB200_TC_STAGES_NARROW
 #define GB200_TC_STAGES_NARROW 4
 #endif
@@ -40,7 +46,7 @@ constexpr int TC_BM = 128, TC_BK = 32, TC_THREADS = 192;
 // issues hi.hi + hi.lo + lo.hi -- fp32-grade products (2^-22) for the forward / input-gradient GEMMs of 'x3' mode that no
 // fused kernel covers; stages are twice as large, so the ring is one stage shorter
 template <int BN, bool SPLIT = false> __host__ __device__ constexpr int tc_stages() {
-    return SPLIT ? (BN <= 64 ? 3 : 2) : (BN == 192 ? 2 : (BN <= 64 ? GB200_TC_STAGES_NARROW : 3));
+    return SPLIT ? GB200_TC_STAGES_SPLIT : (BN == 192 ? 2 : (BN <= 64 ? GB200_TC_STAGES_NARROW : 3));
 }
 template <int BN> __host__ __device__ constexpr int tc_tmem_cols() { return BN == 192 ? 256 : BN; }     // power of two >= 32
 template <int BN, bool SPLIT = false> __host__ __device__ constexpr int tc_smem_bytes() {
@@ -864,6 +870,8 @@ extern "C" int gb200_gemm_tc(int device, const float* A, int lda, int transA, co
     static const int use_persistent = env_int("GB200_TC_PERSISTENT", 0);   // measured equal/slower in the full step
     const bool persistent = use_persistent && g.ksplit == 1 && !g.ep.hn_dk && !g.ep.G;
     if (bn == 192 && (persistent || g.ep.hn_dk || split)) bn = 128;
+    static const int split_bn_cap = env_int("GB200_TC_SPLIT_BN", 64);
+    if (split && !persistent && bn > split_bn_cap && (long long)cdiv(M, TC_BM) * cdiv(N, split_bn_cap) >= 2 * 148) bn = split_bn_cap;
     CUtensorMap ma, mb;
     const CUtensorMapSwizzle SWK = CU_TENSOR_MAP_SWIZZLE_128B, SWMN = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
     bool ok = a_mn ? make_map(&ma, A, M, K, lda, 32, 32, SWMN) : make_map(&ma, A, K, M, lda, 32, TC_BM, SWK);
@@ -952,7 +960,10 @@ extern "C" int gb200_gemm_tc_wgrad_group(int device, int n, const gb200_wgrad_pr
                    "gb200_gemm_tc_wgrad_group: problem %d is not TMA / float4 aligned", i);
         tiles += cdiv(q.M, TC_BM) * cdiv(q.N, 128);
     }
-    int S = (2 * 148) / tiles;
+    // Grid size: two CTAs per SM over the whole GPU.  A smaller grid that would fit on the 28 SMs the fused encoder kernels
+    // leave free was measured (GB200_WGRAD_CTAS=56/112: 4.66/4.68 ms per C3 step against 4.61) -- filling the GPU wins.
+    static const int target = env_int("GB200_WGRAD_CTAS", 296);
+    int S = target / tiles;
     if (S < 1) S = 1;
     if (S > 64) S = 64;
     size_t woff = 0;

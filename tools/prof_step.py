@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--precision", default="x3")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--top", type=int, default=45)
+    ap.add_argument("--timeline", default="", help="write every kernel of the LAST profiled step, in start order, to this file")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     G.set_precision(args.precision)
@@ -41,6 +42,15 @@ def main():
         for _ in range(args.steps):
             step()
         torch.cuda.synchronize()
+    if args.timeline:
+        evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.device_time > 0]
+        evs.sort(key=lambda e: e.time_range.start)
+        per = len(evs) // args.steps
+        evs = evs[-per:]
+        t0 = evs[0].time_range.start
+        with open(args.timeline, "w") as f:
+            for e in evs:
+                f.write(f"{e.time_range.start - t0:10.1f} {e.device_time:8.1f}  {e.name[:100]}\n")
     rows = []
     total = 0.0
     for e in prof.key_averages():
