@@ -495,15 +495,24 @@ __global__ void tc_splitk_reduce_group_kernel(const __grid_constant__ TcGroup G)
 //   warp 0: TMA producer | warp 1: MMA issuer | warps 2-5: TF32 round-to-nearest converters |
 //   warps 6-13: epilogue (two warps per 32-lane TMEM quarter, each taking half of the tile's columns)
 // ---------------------------------------------------------------------------------------------------------
-constexpr int TCP_STAGES = 4, TCP_EPI_WARPS = 8, TCP_THREADS = (6 + TCP_EPI_WARPS) * 32;
+constexpr int TCP_EPI_WARPS = 8, TCP_THREADS = (6 + TCP_EPI_WARPS) * 32;
+// ring depth: as many stages as fit beside the epilogue staging tile; split (3xTF32) stages carry a hi and a lo copy
+template <int BN, bool SPLIT> __host__ __device__ constexpr int tcp_stages() {
+    return !SPLIT ? 4 : (BN <= 32 ? 4 : (BN <= 64 ? 3 : 2));
+}
+template <int BN, bool SPLIT> __host__ __device__ constexpr int tcp_smem_bytes() {
+    return tcp_stages<BN, SPLIT>() * (SPLIT ? 2 : 1) * (TC_BM * TC_BK * 4 + BN * TC_BK * 4) + TC_BM * (BN + 4) * 4 + 1024 + 256;
+}
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool SPLIT = false>
 __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                             const __grid_constant__ CUtensorMap mapB,
                                                                             TcArgs g) {
     constexpr int A_BYTES = TC_BM * TC_BK * 4;
     constexpr int B_BYTES = BN * TC_BK * 4;
-    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int TILE_PAIR = A_BYTES + B_BYTES;               // what TMA lands per k-block
+    constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * TILE_PAIR;   // SPLIT: [A hi | B hi | A lo | B lo]
+    constexpr int TCP_STAGES = tcp_stages<BN, SPLIT>();
     constexpr int DS = BN + 4;
     constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;      // two accumulator buffers (power of two >= 32)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -559,7 +568,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_persistent_kernel(cons
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* sa = smem + s * STAGE_BYTES;
                     uint8_t* sb = sa + A_BYTES;
-                    mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                    mbar_expect_tx(&full_bar[s], TILE_PAIR);
                     const int k0 = kb * TC_BK;
                     if (!A_MN) {
                         tma_load_2d(sa, &mapA, &full_bar[s], k0, m0);
@@ -599,6 +608,13 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_persistent_kernel(cons
                         const uint64_t ad = A_MN ? umma_desc<1>(sa + k * 1024, 4096, 512) : umma_desc<2>(sa + k * 32, 16, 1024);
                         const uint64_t bd = B_MN ? umma_desc<1>(sb + k * 1024, 4096, 512) : umma_desc<2>(sb + k * 32, 16, 1024);
                         tc_mma_tf32(tacc, ad, bd, idesc, (kb | k) != 0);
+                        if (SPLIT) {
+                            const uint32_t la = sa + TILE_PAIR, lb = sb + TILE_PAIR;
+                            const uint64_t adl = A_MN ? umma_desc<1>(la + k * 1024, 4096, 512) : umma_desc<2>(la + k * 32, 16, 1024);
+                            const uint64_t bdl = B_MN ? umma_desc<1>(lb + k * 1024, 4096, 512) : umma_desc<2>(lb + k * 32, 16, 1024);
+                            tc_mma_tf32(tacc, ad, bdl, idesc, 1u);
+                            tc_mma_tf32(tacc, adl, bd, idesc, 1u);
+                        }
                     }
                     tc_commit(&empty_bar[s]);
                 }
@@ -615,7 +631,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_persistent_kernel(cons
                 mbar_wait(&full_bar[s], ph);
                 float4* tile = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
 #pragma unroll 4
-                for (int i = ct; i < STAGE_BYTES / 16; i += 128) {
+                for (int i = ct; i < TILE_PAIR / 16; i += 128) {
                     float4 v = tile[i];
                     uint32_t x, y, z, w;
                     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(x) : "f"(v.x));
@@ -624,6 +640,15 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_persistent_kernel(cons
                     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(w) : "f"(v.w));
                     tile[i] = make_float4(__uint_as_float(x), __uint_as_float(y), __uint_as_float(z),
                                           __uint_as_float(w));
+                    if (SPLIT) {       // residual, itself rounded to TF32 (same swizzled position in the lo copy)
+                        uint32_t a, b, c, d;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a) : "f"(v.x - __uint_as_float(x)));
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(v.y - __uint_as_float(y)));
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(c) : "f"(v.z - __uint_as_float(z)));
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(d) : "f"(v.w - __uint_as_float(w)));
+                        tile[i + TILE_PAIR / 16] = make_float4(__uint_as_float(a), __uint_as_float(b), __uint_as_float(c),
+                                                               __uint_as_float(d));
+                    }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
@@ -678,7 +703,15 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tc_persistent_kernel(cons
             if (rbase < g.M && ncols > 0) {
                 if (g.vec4) {
                     const bool drop = ep.drop_p > 0.f;
-                    if (ep.act == ACT_NONE) {
+                    if (ep.G) {            // gated backward GEMM (host guarantees act none, no residual / accumulate)
+                        if (ep.gate == ACT_RELU) {
+                            if (drop) tc_epilogue_vec4<ACT_NONE, true, false, ACT_RELU>(g, stage, DS, lane, rbase, nc0, ncols, seed);
+                            else tc_epilogue_vec4<ACT_NONE, false, false, ACT_RELU>(g, stage, DS, lane, rbase, nc0, ncols, seed);
+                        } else {
+                            if (drop) tc_epilogue_vec4<ACT_NONE, true, false, ACT_SILU>(g, stage, DS, lane, rbase, nc0, ncols, seed);
+                            else tc_epilogue_vec4<ACT_NONE, false, false, ACT_SILU>(g, stage, DS, lane, rbase, nc0, ncols, seed);
+                        }
+                    } else if (ep.act == ACT_NONE) {
                         if (drop) tc_epilogue_vec4<ACT_NONE, true>(g, stage, DS, lane, rbase, nc0, ncols, seed);
                         else tc_epilogue_vec4<ACT_NONE, false>(g, stage, DS, lane, rbase, nc0, ncols, seed);
                     } else if (ep.act == ACT_RELU) {
@@ -747,12 +780,13 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs&
     return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool SPLIT = false>
 static int launch_tc_persistent(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& g, cudaStream_t st) {
-    constexpr int smem = TCP_STAGES * (TC_BM * TC_BK * 4 + BN * TC_BK * 4) + TC_BM * (BN + 4) * 4 + 1024 + 256;
+    constexpr int smem = tcp_smem_bytes<BN, SPLIT>();
+    static_assert(smem <= 232448, "persistent GEMM: shared memory");
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(gemm_tc_persistent_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(gemm_tc_persistent_kernel<BN, A_MN, B_MN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         configured = true;
     }
     static int num_sms = 0;
@@ -764,7 +798,7 @@ static int launch_tc_persistent(const CUtensorMap& ma, const CUtensorMap& mb, co
     }
     const int tiles = cdiv(g.N, BN) * cdiv(g.M, TC_BM);
     const int grid = tiles < num_sms ? tiles : num_sms;
-    launch_pdl(gemm_tc_persistent_kernel<BN, A_MN, B_MN>, grid, TCP_THREADS, smem, st, ma, mb, g);
+    launch_pdl(gemm_tc_persistent_kernel<BN, A_MN, B_MN, SPLIT>, grid, TCP_THREADS, smem, st, ma, mb, g);
     return 0;
 }
 
@@ -868,10 +902,17 @@ extern "C" int gb200_gemm_tc(int device, const float* A, int lda, int transA, co
                    "gb200_gemm_tc: split-K workspace too small");
     GB_REQUIRE(!g.ep.hn_dk || (g.vec4 && g.ksplit == 1), "gb200_gemm_tc: fused head-norm needs the float4 epilogue");
     static const int use_persistent = env_int("GB200_TC_PERSISTENT", 0);   // measured equal/slower in the full step
-    const bool persistent = use_persistent && g.ksplit == 1 && !g.ep.hn_dk && !g.ep.G;
+    // split (3xTF32) tall-skinny problems -- the decoder's per-pixel linears, 1243 row tiles of a K <= 130 GEMM -- are bound by
+    // per-tile latency (prologue, first TMA, epilogue) in the one-tile-per-CTA kernel: the persistent kernel keeps the ring
+    // streaming across tiles and drains tile i while tile i+1 is loading
+    static const int split_persistent = env_int("GB200_TC_SPLIT_PERSISTENT", 1);
+    const bool sp = split && split_persistent && !a_mn && g.ksplit == 1 && !g.ep.hn_dk && g.vec4 &&
+                    (long long)cdiv(M, TC_BM) * cdiv(N, 128) >= 2 * 148;
+    const bool persistent = sp || (use_persistent && !split && g.ksplit == 1 && !g.ep.hn_dk && !g.ep.G);
     if (bn == 192 && (persistent || g.ep.hn_dk || split)) bn = 128;
     static const int split_bn_cap = env_int("GB200_TC_SPLIT_BN", 64);
     if (split && !persistent && bn > split_bn_cap && (long long)cdiv(M, TC_BM) * cdiv(N, split_bn_cap) >= 2 * 148) bn = split_bn_cap;
+    if (sp) bn = N >= 128 ? 128 : (N >= 64 ? 64 : 32);
     CUtensorMap ma, mb;
     const CUtensorMapSwizzle SWK = CU_TENSOR_MAP_SWIZZLE_128B, SWMN = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
     bool ok = a_mn ? make_map(&ma, A, M, K, lda, 32, 32, SWMN) : make_map(&ma, A, K, M, lda, 32, TC_BM, SWK);
@@ -894,7 +935,17 @@ extern "C" int gb200_gemm_tc(int device, const float* A, int lda, int transA, co
             else launch_tc<BNV, true, true>(ma, mb, g, st);                                       \
         }                                                                                         \
     } while (0)
-    if (split && !persistent) {
+    if (sp) {
+#define TC_SPLIT_P(BNV)                                                                         \
+    do {                                                                                        \
+        if (!b_mn) launch_tc_persistent<BNV, false, false, true>(ma, mb, g, st);                \
+        else launch_tc_persistent<BNV, false, true, true>(ma, mb, g, st);                       \
+    } while (0)
+        if (bn == 128) TC_SPLIT_P(128);
+        else if (bn == 64) TC_SPLIT_P(64);
+        else TC_SPLIT_P(32);
+#undef TC_SPLIT_P
+    } else if (split && !persistent) {
 #define TC_SPLIT(BNV)                                                                  \
     do {                                                                               \
         if (!a_mn && !b_mn) launch_tc<BNV, false, false, true>(ma, mb, g, st);         \

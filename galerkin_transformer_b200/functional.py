@@ -1318,6 +1318,18 @@ class _SpectralConvFn(torch.autograd.Function):
                     ptr(z), Co, None, Co, ptr(gz), Co, P, Co, act, 1.0, 0.0, 0, ptr(dbl), ptr(wsp), wsb, st)
         else:
             gz = epilogue_bwd(gy, P, Co, z=z, act=act) if act != 0 else gy
+        # parameter gradients leave the critical path (side streams, joined at the end of this node): the pointwise weight
+        # needs only gz, the spectral weights only dO^
+        fork = _Fork(gz)
+        dwl = None
+        if ctx.needs_input_grad[2]:
+            dwl = torch.empty_like(wl)
+            with fork.side(0):
+                gemm(gz, x, dwl, Co, Ci, P, lda=Co, ldb=Ci, ldc=Ci, transA=True, wgrad=True)
+        if dbl is None and has_bias and ctx.needs_input_grad[3]:
+            dbl = torch.empty(Co, dtype=torch.float32, device=x.device)
+            with fork.side(0):
+                colsum(gz, P, Co, Co, dbl)
         # adjoint of the inverse transform:  dO^ = (c_ky s) * DFT(gz) on the kept modes
         if two_d:
             dZ = _ydft(gz, B * n, n, Co, m, twY, 1.0 / n, True)
@@ -1329,9 +1341,14 @@ class _SpectralConvFn(torch.autograd.Function):
         dfw0 = torch.empty_like(fw0) if ctx.needs_input_grad[4] else None
         dfw1 = torch.empty_like(fw1) if (fw1 is not None and dfw0 is not None) else None
         mix_work = (16.0 * B * halves * M2 * Ci * Co, 8.0 * halves * M2 * (2 * Ci * Co + 2 * B * (Ci + Co)))
-        _launch("spectral_mix", *mix_work, lib.gb200_spectral_mix_bwd, dev, ptr(Xf), ptr(dO), ptr(fw0), ptr(fw1), B,
-                halves, M2, Ci, Co, ptr(dXf), ptr(dfw0), ptr(dfw1), 0, st)
-        dx = dxf = dwl = None
+        if dfw0 is not None:
+            with fork.side(1):
+                _launch("spectral_mix", mix_work[0] / 2, mix_work[1] / 2, lib.gb200_spectral_mix_bwd, dev, ptr(Xf), ptr(dO),
+                        ptr(fw0), ptr(fw1), B, halves, M2, Ci, Co, None, ptr(dfw0), ptr(dfw1), 0, stream_of(dO))
+        if dXf is not None:
+            _launch("spectral_mix", mix_work[0] / 2, mix_work[1] / 2, lib.gb200_spectral_mix_bwd, dev, ptr(Xf), ptr(dO),
+                    ptr(fw0), ptr(fw1), B, halves, M2, Ci, Co, ptr(dXf), None, None, 0, st)
+        dx = dxf = None
         if need_dx:
             # adjoint of the forward transform + the pointwise path  gz @ Wl, one fused kernel
             wres = wl if same else torch.zeros_like(wl)
@@ -1345,12 +1362,7 @@ class _SpectralConvFn(torch.autograd.Function):
                 dxf = dx
                 dx = torch.empty_like(x)
                 gemm(gz, wl, dx, P, Ci, Co, lda=Co, ldb=Ci, ldc=Ci)
-        if ctx.needs_input_grad[2]:
-            dwl = torch.empty_like(wl)
-            gemm(gz, x, dwl, Co, Ci, P, lda=Co, ldb=Ci, ldc=Ci, transA=True, wgrad=True)
-        if dbl is None and has_bias and ctx.needs_input_grad[3]:
-            dbl = torch.empty(Co, dtype=torch.float32, device=x.device)
-            colsum(gz, P, Co, Co, dbl)
+        fork.join()
         return dx, dxf, dwl, dbl, dfw0, dfw1, None, None, None
 
 
