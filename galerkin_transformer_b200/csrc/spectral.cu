@@ -333,6 +333,290 @@ __global__ void __launch_bounds__(256) yidft_epi_kernel(
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Row kernels for 2-D grids (many short rows: R = B*n rows of n <= ~1000 points).  Same arithmetic as the kernels above
+// (fp32 FMAs, sequential sums), restructured so that shared-memory traffic and load latency stop binding:
+//   ydft_row    CTA = one row: the whole row and the twiddle table are staged once (all global loads in flight together),
+//               a thread owns 3 modes of one channel and consumes 4 points per step with float4 twiddle reads
+//   xdft_rows   CTA = (b, ky, 6 modes kx): 4 thread groups split X, 4 loads in flight each, shared-memory reduction
+//   xidft_rows  CTA = (b, ky, 36 X): the (2m x C) coefficient column is staged once and reused for every X
+//   yidft_row   register tile of 4 points x 4 channels per thread: each float4 read from shared memory feeds 16 FMAs
+//               (the kernel above: 4) -- it was bound by shared-memory bandwidth at 18% of the FMA rate
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int YR_KPT = 3;
+
+__global__ void __launch_bounds__(128) ydft_row_kernel(const float* __restrict__ x, int n, int NP, int C, int m,
+                                                       const float2* __restrict__ twY, float scale, int hermitian,
+                                                       float2* __restrict__ out) {
+    pdl_enter();
+    extern __shared__ __align__(16) float sm[];
+    float* xs = sm;                  // [NP][C], rows >= n are zero
+    float* twc = xs + NP * C;        // [m][NP]
+    float* tws = twc + m * NP;       // [m][NP]
+    const long long R = blockIdx.x;
+    const float4* x4 = reinterpret_cast<const float4*>(x + R * n * C);
+    const int n4 = n * C / 4, np4 = NP * C / 4;
+#pragma unroll 4
+    for (int e = threadIdx.x; e < np4; e += 128)
+        reinterpret_cast<float4*>(xs)[e] = e < n4 ? x4[e] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = threadIdx.x; e < m * NP; e += 128) {
+        const int ky = e / NP, y = e % NP;
+        const float2 t = y < n ? twY[(long long)ky * n + y] : make_float2(0.f, 0.f);
+        twc[e] = t.x;
+        tws[e] = t.y;
+    }
+    __syncthreads();
+    const int nkg = (m + YR_KPT - 1) / YR_KPT;
+    for (int item = threadIdx.x; item < C * nkg; item += 128) {
+        const int c = item % C, k0 = (item / C) * YR_KPT;
+        float are[YR_KPT], aim[YR_KPT];
+        const float *pc[YR_KPT], *ps[YR_KPT];
+#pragma unroll
+        for (int j = 0; j < YR_KPT; ++j) {
+            are[j] = 0.f; aim[j] = 0.f;
+            const int kk = min(k0 + j, m - 1);
+            pc[j] = twc + kk * NP;
+            ps[j] = tws + kk * NP;
+        }
+        const float* xp = xs + c;
+#pragma unroll 2
+        for (int y = 0; y < NP; y += 4) {
+            const float v0 = xp[y * C], v1 = xp[(y + 1) * C], v2 = xp[(y + 2) * C], v3 = xp[(y + 3) * C];
+#pragma unroll
+            for (int j = 0; j < YR_KPT; ++j) {
+                const float4 cc = *reinterpret_cast<const float4*>(pc[j] + y);
+                const float4 ss = *reinterpret_cast<const float4*>(ps[j] + y);
+                are[j] = fmaf(v0, cc.x, are[j]); aim[j] = fmaf(-v0, ss.x, aim[j]);
+                are[j] = fmaf(v1, cc.y, are[j]); aim[j] = fmaf(-v1, ss.y, aim[j]);
+                are[j] = fmaf(v2, cc.z, are[j]); aim[j] = fmaf(-v2, ss.z, aim[j]);
+                are[j] = fmaf(v3, cc.w, are[j]); aim[j] = fmaf(-v3, ss.w, aim[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < YR_KPT; ++j) {
+            const int ky = k0 + j;
+            if (ky < m) {
+                const float sc = scale * (hermitian ? herm_weight(ky, n) : 1.f);
+                out[(R * m + ky) * C + c] = make_float2(are[j] * sc, aim[j] * sc);
+            }
+        }
+    }
+}
+
+constexpr int XD_RG = 6;    // modes kx per CTA
+
+__global__ void __launch_bounds__(128) xdft_rows_kernel(const float2* __restrict__ T1, int n, int m, int C,
+                                                        const float2* __restrict__ twX, float scale,
+                                                        float2* __restrict__ out) {
+    pdl_enter();
+    __shared__ float2 red[3][XD_RG][32];
+    extern __shared__ __align__(16) float2 tw2[];          // [XD_RG][n]
+    const int r0 = blockIdx.x * XD_RG, ky = blockIdx.y, b = blockIdx.z;
+    const int nr = min(XD_RG, 2 * m - r0);
+    for (int e = threadIdx.x; e < XD_RG * n; e += 128) {
+        const int j = e / n, X = e % n;
+        tw2[e] = j < nr ? twX[(long long)(r0 + j) * n + X] : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    const int cl = threadIdx.x % 32, xq = threadIdx.x / 32;
+    const long long xstride = (long long)m * C;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+        const int c = c0 + cl;
+        const bool cok = c < C;
+        float are[XD_RG], aim[XD_RG];
+#pragma unroll
+        for (int j = 0; j < XD_RG; ++j) { are[j] = 0.f; aim[j] = 0.f; }
+        const float2* tp = T1 + (((long long)b * n) * m + ky) * C + (cok ? c : 0);
+        for (int X0 = xq; X0 < n; X0 += 16) {
+            float2 t[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int X = X0 + 4 * u;
+                t[u] = (cok && X < n) ? tp[X * xstride] : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int X = min(X0 + 4 * u, n - 1);          // t[u] is zero past the end
+#pragma unroll
+                for (int j = 0; j < XD_RG; ++j) {
+                    const float2 w = tw2[j * n + X];
+                    are[j] = fmaf(t[u].x, w.x, fmaf(t[u].y, w.y, are[j]));
+                    aim[j] = fmaf(t[u].y, w.x, fmaf(-t[u].x, w.y, aim[j]));
+                }
+            }
+        }
+        if (xq > 0) {
+#pragma unroll
+            for (int j = 0; j < XD_RG; ++j) red[xq - 1][j][cl] = make_float2(are[j], aim[j]);
+        }
+        __syncthreads();
+        if (xq == 0 && cok) {
+#pragma unroll
+            for (int j = 0; j < XD_RG; ++j) {
+                if (j < nr) {
+                    float sr = are[j], si = aim[j];
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) { sr += red[q][j][cl].x; si += red[q][j][cl].y; }
+                    out[(((long long)b * 2 * m + r0 + j) * m + ky) * C + c] = make_float2(sr * scale, si * scale);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+constexpr int XI_XC = 36;   // X per CTA: 4 thread groups x 3 passes x 3 X per pass
+
+__global__ void __launch_bounds__(128) xidft_rows_kernel(const float2* __restrict__ Oft, int n, int m, int C,
+                                                         const float2* __restrict__ twX, float scale,
+                                                         float2* __restrict__ Z) {
+    pdl_enter();
+    extern __shared__ __align__(16) float2 sm2[];
+    float2* Os = sm2;                       // [2m][32]   one 32-channel block of O^[b, :, ky, :]
+    float2* tw = Os + 2 * m * 32;           // [2m][XI_XC]
+    const int x0 = blockIdx.x * XI_XC, ky = blockIdx.y, b = blockIdx.z;
+    const int m2 = 2 * m;
+    for (int e = threadIdx.x; e < m2 * XI_XC; e += 128) {
+        const int r = e / XI_XC, X = x0 + e % XI_XC;
+        tw[e] = X < n ? twX[(long long)r * n + X] : make_float2(0.f, 0.f);
+    }
+    const int cl = threadIdx.x % 32, xq = threadIdx.x / 32;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < m2 * 32; e += 128) {
+            const int r = e / 32, cc = c0 + e % 32;
+            Os[e] = cc < C ? Oft[(((long long)b * m2 + r) * m + ky) * C + cc] : make_float2(0.f, 0.f);
+        }
+        __syncthreads();
+        const int c = c0 + cl;
+        for (int i0 = xq; i0 < XI_XC; i0 += 12) {
+            float zr[3] = {0.f, 0.f, 0.f}, zi[3] = {0.f, 0.f, 0.f};
+#pragma unroll 4
+            for (int r = 0; r < m2; ++r) {
+                const float2 o = Os[r * 32 + cl];
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    const float2 w = tw[r * XI_XC + i0 + 4 * u];
+                    zr[u] = fmaf(o.x, w.x, fmaf(-o.y, w.y, zr[u]));
+                    zi[u] = fmaf(o.x, w.y, fmaf(o.y, w.x, zi[u]));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int X = x0 + i0 + 4 * u;
+                if (X < n && c < C) Z[(((long long)b * n + X) * m + ky) * C + c] = make_float2(zr[u] * scale, zi[u] * scale);
+            }
+        }
+    }
+}
+
+template <int YG>
+__global__ void __launch_bounds__(512) yidft_row_kernel(
+    const float2* __restrict__ Z, int n, int m, int Co, const float2* __restrict__ twY, float scale, int hermitian,
+    const float* __restrict__ x2, int Ci, const float* __restrict__ Wm, const float* __restrict__ bias, int act,
+    float* __restrict__ y, float* __restrict__ zout, int tiles_per_cta) {
+    pdl_enter();
+    constexpr int YT = 4 * YG;
+    extern __shared__ __align__(16) float sm[];
+    const int XP = Ci + 4;                 // row pitch of the x tile: rows yg..yg+3 of a warp fall in distinct banks
+    float* zre = sm;                       // [m][Co]   c_ky * scale * Re Z
+    float* zim = zre + m * Co;             // [m][Co]  -c_ky * scale * Im Z
+    float* Ws = zim + m * Co;              // [Ci][Co]
+    float* twc = Ws + Ci * Co;             // [m][YT]   column p = 4*yg + j  <->  point yg + YG*j
+    float* tws = twc + m * YT;             // [m][YT]
+    float* xs = tws + m * YT;              // [YT][XP]
+    const int OG = Co / 4;
+    const int og = threadIdx.x % OG, yg = threadIdx.x / OG;
+    const long long R = blockIdx.x;
+    for (int e = threadIdx.x; e < m * Co; e += blockDim.x) {
+        const int ky = e / Co;
+        const float s = scale * (hermitian ? herm_weight(ky, n) : 1.f);
+        const float2 z = Z[R * m * Co + e];
+        zre[e] = z.x * s;
+        zim[e] = -z.y * s;
+    }
+    for (int e = threadIdx.x; e < Ci * Co / 4; e += blockDim.x)
+        reinterpret_cast<float4*>(Ws)[e] = reinterpret_cast<const float4*>(Wm)[e];
+    const float4 bb = bias ? *reinterpret_cast<const float4*>(bias + 4 * og) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int c4 = Ci / 4;
+    const int tile0 = blockIdx.y * tiles_per_cta;
+    for (int tile = tile0; tile < tile0 + tiles_per_cta; ++tile) {
+        const int y0 = tile * YT;
+        if (y0 >= n) break;
+        __syncthreads();
+        for (int e = threadIdx.x; e < m * YT; e += blockDim.x) {
+            const int ky = e / YT, p = e % YT;
+            const int Y = y0 + (p >> 2) + YG * (p & 3);
+            const float2 t = Y < n ? twY[(long long)ky * n + Y] : make_float2(0.f, 0.f);
+            twc[e] = t.x;
+            tws[e] = t.y;
+        }
+        for (int e = threadIdx.x; e < YT * c4; e += blockDim.x) {
+            const int r = e / c4, q = e % c4;
+            const int Y = y0 + r;
+            *reinterpret_cast<float4*>(xs + r * XP + 4 * q) =
+                Y < n ? *reinterpret_cast<const float4*>(x2 + ((R * n) + Y) * Ci + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();
+        float acc[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int o = 0; o < 4; ++o) acc[j][o] = 0.f;
+        for (int ky = 0; ky < m; ++ky) {
+            const float4 zr = *reinterpret_cast<const float4*>(zre + ky * Co + 4 * og);
+            const float4 zi = *reinterpret_cast<const float4*>(zim + ky * Co + 4 * og);
+            const float4 cc = *reinterpret_cast<const float4*>(twc + ky * YT + 4 * yg);
+            const float4 ss = *reinterpret_cast<const float4*>(tws + ky * YT + 4 * yg);
+            const float cj[4] = {cc.x, cc.y, cc.z, cc.w}, sj[4] = {ss.x, ss.y, ss.z, ss.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                acc[j][0] = fmaf(zr.x, cj[j], fmaf(zi.x, sj[j], acc[j][0]));
+                acc[j][1] = fmaf(zr.y, cj[j], fmaf(zi.y, sj[j], acc[j][1]));
+                acc[j][2] = fmaf(zr.z, cj[j], fmaf(zi.z, sj[j], acc[j][2]));
+                acc[j][3] = fmaf(zr.w, cj[j], fmaf(zi.w, sj[j], acc[j][3]));
+            }
+        }
+        for (int i4 = 0; i4 < c4; ++i4) {
+            float xv[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 v = *reinterpret_cast<const float4*>(xs + (yg + YG * j) * XP + 4 * i4);
+                xv[j][0] = v.x; xv[j][1] = v.y; xv[j][2] = v.z; xv[j][3] = v.w;
+            }
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) {
+                const float4 w = *reinterpret_cast<const float4*>(Ws + (4 * i4 + ii) * Co + 4 * og);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    acc[j][0] = fmaf(xv[j][ii], w.x, acc[j][0]);
+                    acc[j][1] = fmaf(xv[j][ii], w.y, acc[j][1]);
+                    acc[j][2] = fmaf(xv[j][ii], w.z, acc[j][2]);
+                    acc[j][3] = fmaf(xv[j][ii], w.w, acc[j][3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int Y = y0 + yg + YG * j;
+            if (Y < n) {
+                const float4 v = make_float4(acc[j][0] + bb.x, acc[j][1] + bb.y, acc[j][2] + bb.z, acc[j][3] + bb.w);
+                const long long idx = ((R * n) + Y) * Co + 4 * og;
+                if (zout) *reinterpret_cast<float4*>(zout + idx) = v;
+                *reinterpret_cast<float4*>(y + idx) =
+                    make_float4(act_apply(act, v.x), act_apply(act, v.y), act_apply(act, v.z), act_apply(act, v.w));
+            }
+        }
+    }
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static int spectral_rows_enabled() {
+    static const int on = [] { const char* v = getenv("GB200_SPECTRAL_ROWS"); return v ? atoi(v) : 1; }();
+    return on;
+}
+
 }  // namespace gb200
 
 using namespace gb200;
@@ -379,6 +663,18 @@ extern "C" int gb200_spectral_ydft(int device, const float* x, long long R, int 
 #undef YD
         return check_launch("gb200_spectral_ydft");
     }
+    {
+        const int NP = (n + 3) / 4 * 4;
+        const size_t smem = (size_t)(NP * C + 2 * m * NP) * sizeof(float);
+        if (spectral_rows_enabled() && nsplit == 1 && C % 4 == 0 && R >= 148 && R <= 0x7fffffffLL && smem <= 96 * 1024 &&
+            aligned16(x)) {
+            if (smem > 48 * 1024)
+                cudaFuncSetAttribute(ydft_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            launch_pdl(ydft_row_kernel, dim3((unsigned)R), 128, smem, st, x, n, NP, C, m,
+                       reinterpret_cast<const float2*>(twY), scale, hermitian, reinterpret_cast<float2*>(out));
+            return check_launch("gb200_spectral_ydft");
+        }
+    }
     const long long RC = R * C;
     int ychunk = cdiv(cdiv(n, nsplit), YCH) * YCH;
     nsplit = cdiv(n, ychunk);
@@ -403,6 +699,25 @@ extern "C" int gb200_spectral_xdft(int device, const float* T1, int B, int n, in
     GB_REQUIRE(T1 && twX && out && B >= 1 && n >= 1 && m >= 1 && C >= 1, "gb200_spectral_xdft: bad arguments");
     GB_REQUIRE(2 * m <= n, "gb200_spectral_xdft: 2*modes=%d exceeds n=%d (mode blocks would overlap)", 2 * m, n);
     cudaStream_t st = as_stream(stream);
+    if (spectral_rows_enabled() && B <= 65535 && m <= 65535) {
+        if (!inverse) {
+            const size_t smem = (size_t)XD_RG * n * sizeof(float2);
+            if (smem <= 40 * 1024) {
+                launch_pdl(xdft_rows_kernel, dim3(cdiv(2 * m, XD_RG), m, B), 128, smem, st,
+                           reinterpret_cast<const float2*>(T1), n, m, C, reinterpret_cast<const float2*>(twX), scale,
+                           reinterpret_cast<float2*>(out));
+                return check_launch("gb200_spectral_xdft");
+            }
+        } else {
+            const size_t smem = (size_t)2 * m * (32 + XI_XC) * sizeof(float2);
+            if (smem <= 48 * 1024) {
+                launch_pdl(xidft_rows_kernel, dim3(cdiv(n, XI_XC), m, B), 128, smem, st,
+                           reinterpret_cast<const float2*>(T1), n, m, C, reinterpret_cast<const float2*>(twX), scale,
+                           reinterpret_cast<float2*>(out));
+                return check_launch("gb200_spectral_xdft");
+            }
+        }
+    }
     if (!inverse) {
         long long total = (long long)B * 2 * m * m * C;
         launch_pdl(xdft_kernel, cdiv(total, 128), 128, 0, st, reinterpret_cast<const float2*>(T1), B, n, m, C,
@@ -491,6 +806,33 @@ extern "C" int gb200_spectral_yidft_epilogue(int device, const float* Z, long lo
             switch (nt) { case 1: YI(1); break; case 2: YI(2); break; case 3: YI(3); break; case 4: YI(4); break;
                           case 5: YI(5); break; case 6: YI(6); break; case 7: YI(7); break; default: YI(8); }
 #undef YI
+            return check_launch("gb200_spectral_yidft_epilogue");
+        }
+    }
+    if (spectral_rows_enabled() && Co % 8 == 0 && Co <= 128 && Ci % 4 == 0 && R >= 148 && aligned16(x2) && aligned16(Wm) &&
+        aligned16(y) && (!zout || aligned16(zout)) && (!bias || aligned16(bias))) {
+        const int OG = Co / 4;
+        const int pad12 = cdiv(n, 48) * 48, pad16 = cdiv(n, 64) * 64;
+        const int YG = (pad12 <= pad16 && (12 * OG) % 32 == 0 && 12 * OG <= 512) ? 12 : 16;
+        const int YTr = 4 * YG, threads = YG * OG;
+        const size_t smr = (size_t)(2 * m * Co + Ci * Co + 2 * m * YTr + YTr * (Ci + 4)) * sizeof(float);
+        if (threads <= 512 && threads % 32 == 0 && smr <= 64 * 1024) {
+            const int ntl = cdiv(n, YTr);
+            int tpc = ntl;
+            while (tpc > 1 && R * cdiv(ntl, tpc) < 4 * 148) tpc = (tpc + 1) / 2;
+            dim3 gridr((unsigned)R, cdiv(ntl, tpc));
+            cudaStream_t str = as_stream(stream);
+            if (YG == 12) {
+                if (smr > 48 * 1024)
+                    cudaFuncSetAttribute(yidft_row_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr);
+                launch_pdl(yidft_row_kernel<12>, gridr, threads, smr, str, reinterpret_cast<const float2*>(Z), n, m, Co,
+                           reinterpret_cast<const float2*>(twY), scale, hermitian, x2, Ci, Wm, bias, act, y, zout, tpc);
+            } else {
+                if (smr > 48 * 1024)
+                    cudaFuncSetAttribute(yidft_row_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr);
+                launch_pdl(yidft_row_kernel<16>, gridr, threads, smr, str, reinterpret_cast<const float2*>(Z), n, m, Co,
+                           reinterpret_cast<const float2*>(twY), scale, hermitian, x2, Ci, Wm, bias, act, y, zout, tpc);
+            }
             return check_launch("gb200_spectral_yidft_epilogue");
         }
     }

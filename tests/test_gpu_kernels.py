@@ -397,6 +397,8 @@ def _sc_ref(x, wl, bl, fw0, fw1, m, act, two_d):
 
 @pytest.mark.parametrize("shape,Co,m,act", [((2, 15, 15, 6), 5, 4, "silu"), ((1, 32, 32, 20), 20, 12, "silu"),
                                             ((2, 141, 141, 8), 8, 12, "relu"), ((3, 16, 16, 4), 7, 8, "none"),
+                                            ((2, 141, 141, 32), 32, 12, "silu"), ((1, 150, 150, 16), 24, 9, "silu"),
+                                            ((5, 40, 40, 12), 8, 16, "none"),
                                             ((2, 64, 8), 6, 5, "silu"), ((2, 8192, 16), 12, 16, "silu"),
                                             ((3, 45, 4), 4, 7, "relu"), ((1, 40, 3), 3, 20, "none")])
 @pytest.mark.parametrize("prec", ["fp32", "tf32"])
