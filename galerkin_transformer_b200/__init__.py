@@ -12,5 +12,6 @@ from .model import (DownScaler, FourierTransformer2D, FourierTransformer2DLite, 
                     SpectralRegressor, UpScaler)
 from .functional import get_precision, set_precision  # noqa: F401
 from .utils import scaler_sizes, set_attn_dropout  # noqa: F401
+from .train import FusedAdam, WeightedL2Loss2d, one_cycle, train_batch_darcy  # noqa: F401
 
 __version__ = "0.1.0"

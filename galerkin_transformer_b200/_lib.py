@@ -93,6 +93,12 @@ SIGNATURES = {
                                c_ull, c_vp, c_int, c_vp, c_sz, c_int, c_vp]),
     "gb200_interp_bilinear_fwd": (c_int, [c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp]),
     "gb200_interp_bilinear_bwd": (c_int, [c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp]),
+    "gb200_weighted_l2_loss2d_workspace_bytes": (c_sz, [c_int, c_int]),
+    "gb200_weighted_l2_loss2d": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_float, c_float, c_float, c_float,
+                                         c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "gb200_adam_clip_step_workspace_bytes": (c_sz, [c_ll]),
+    "gb200_adam_clip_step": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_ll, c_vp, c_float, c_float, c_float, c_float, c_vp,
+                                     c_vp, c_sz, c_vp]),
     "gb200_philox_scale": (c_int, [c_int, c_vp, c_ll, c_float, c_ull, c_vp]),
     "gb200_attn_xm": (c_int, [c_int, _HOP, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp,
                               c_int, c_int, c_int, c_float, c_int, c_vp]),

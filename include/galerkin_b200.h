@@ -350,6 +350,35 @@ size_t gb200_conv1_bwd_workspace_bytes(int C);
 int gb200_conv1_bwd(int device, const float* dy, const float* y, const float* x, const float* w, float* dx, float* dw, int B,
                     int H, int W, int C, float p, float* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ training-step tail ---------
+ * SURVEY.md 8(f) row 3.  csrc/train.cu.
+ *
+ * gb200_weighted_l2_loss2d: WeightedL2Loss2d.forward(preds, targets, targets_prime=..., K=...) of libs/ft.py:1035-1101
+ * for preds / targets (B, n, n), targets_prime (B, n, n, 2) or NULL, K (B, n, n) or NULL (K = 1):
+ *   loss_b = beta * mean((p - t)^2) / (mean(t^2) + eps);  loss = mean_b sqrt(loss_b)   (return_norm; else mean_b loss_b)
+ *   reg_b  = gamma * h * mean((K (tp - D_h p))^2) / (2 mean(K tp^2) + eps) over the interior (regularizer != 0 and
+ *            targets_prime given; D_h = central differences with the given even dilation), reduced like the loss
+ *   out4   = { loss, regularizer, 'L1' metric = mean_b sqrt(loss_b), loss + regularizer }         (device floats)
+ *   dloss / dreg (either may be NULL) = the gradients of out4[0] / out4[1] with respect to preds -- what autograd through
+ *   the reference's ~40 elementwise launches produces.  Two launches, fixed-order reductions, no host synchronisation.
+ *
+ * gb200_adam_clip_step: nn.utils.clip_grad_norm_(params, max_norm) followed by torch.optim.Adam.step()
+ * (libs/utils_ft.py:676-681) over FLAT fp32 buffers of n elements: total = |grad|_2, g *= min(1, max_norm / (total + 1e-6))
+ * (max_norm <= 0: no clipping), m = lerp(m, g, 1 - beta1), v = beta2 v + (1 - beta2) g^2,
+ * p -= lr / bias_correction1 * m / (sqrt(v) / sqrt(bias_correction2) + eps).
+ * hyper = DEVICE array { lr, beta1, bias_correction1, bias_correction2 } (changes every step under OneCycleLR, which also
+ * cycles beta1; a device array keeps the launches graph-capturable).  grad_norm_out (device float or NULL) receives the
+ * pre-clip norm.  Two launches. */
+size_t gb200_weighted_l2_loss2d_workspace_bytes(int B, int n);
+int gb200_weighted_l2_loss2d(int device, const float* preds, const float* targets, const float* targets_prime,
+                             const float* K, int B, int n, float h, float beta, float gamma, float eps, int dilation,
+                             int regularizer, int return_norm, float* out4, float* dloss, float* dreg, float* workspace,
+                             size_t workspace_bytes, void* stream);
+size_t gb200_adam_clip_step_workspace_bytes(long long n);
+int gb200_adam_clip_step(int device, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                         const float* hyper, float beta2, float eps, float weight_decay, float max_norm,
+                         float* grad_norm_out, float* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
