@@ -146,6 +146,132 @@ __global__ void __launch_bounds__(256) interp_bwd_kernel(InterpArgs a) {
     }
 }
 
+// Table-driven backward for resize ratios up to ~3x (every shipped scaler): the per-axis candidate ranges and weights depend
+// only on the pixel coordinate, so the x table (Win entries) is built once per CTA and the y weights once per row, instead of
+// 16 weight evaluations + 2 range computations per THREAD (the gather above spent ~250 ALU instructions per float4 of output
+// and was issue-bound at ~60-90 us for an 81 MB pass).  A warp covers one pixel's channel run, so every tap test is warp-
+// uniform; the <= 8 candidate columns of a row are fetched as 8 independent predicated float4 loads.
+constexpr int IB_MAXR = 8;
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) interp_bwd_table_kernel(InterpArgs a) {
+    pdl_enter();
+    extern __shared__ __align__(16) float tab[];       // [Win][IB_MAXR] weights, then [Win] first candidate column (int)
+    __shared__ float s_wy[IB_MAXR];
+    __shared__ int s_ylo;
+    float* wxs = tab;
+    int* xlos = reinterpret_cast<int*>(tab + (size_t)a.Win * IB_MAXR);
+    for (int ix = threadIdx.x; ix < a.Win; ix += blockDim.x) {
+        int xlo, xhi;
+        dst_range(a.sx, ix, a.Wout, xlo, xhi);
+        xlos[ix] = xlo;
+#pragma unroll
+        for (int v = 0; v < IB_MAXR; ++v) wxs[ix * IB_MAXR + v] = (xlo + v <= xhi) ? axis_weight(a.sx, xlo + v, a.Win, ix) : 0.f;
+    }
+    const int cq = VEC ? a.C / 4 : a.C;
+    const int rowlen = a.Win * cq;
+    for (int row = blockIdx.x; row < a.B * a.Hin; row += gridDim.x) {
+        const int b = row / a.Hin, iy = row % a.Hin;
+        __syncthreads();
+        if (threadIdx.x < IB_MAXR) {
+            int ylo, yhi;
+            dst_range(a.sy, iy, a.Hout, ylo, yhi);
+            if (threadIdx.x == 0) s_ylo = ylo;
+            s_wy[threadIdx.x] = (ylo + (int)threadIdx.x <= yhi) ? axis_weight(a.sy, ylo + threadIdx.x, a.Hin, iy) : 0.f;
+        }
+        __syncthreads();
+        const int ylo = s_ylo;
+        const long long base = (long long)b * a.Hout * a.Wout;
+        for (int t = threadIdx.x; t < rowlen; t += blockDim.x) {
+            const int ix = t / cq, c = t % cq;
+            const int xlo = xlos[ix];
+            float wx[IB_MAXR];
+#pragma unroll
+            for (int v = 0; v < IB_MAXR; ++v) wx[v] = wxs[ix * IB_MAXR + v];
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+            for (int u = 0; u < IB_MAXR; ++u) {
+                const float wy = s_wy[u];
+                if (wy == 0.f) continue;                               // uniform over the CTA
+                const long long o = (base + (long long)(ylo + u) * a.Wout + xlo) * cq + c;
+                if (VEC) {
+                    float4 g[IB_MAXR];
+#pragma unroll
+                    for (int v = 0; v < IB_MAXR; ++v)
+                        g[v] = wx[v] != 0.f ? reinterpret_cast<const float4*>(a.in)[o + (long long)v * cq]
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int v = 0; v < IB_MAXR; ++v) {
+                        const float w = wy * wx[v];
+                        acc.x = fmaf(w, g[v].x, acc.x); acc.y = fmaf(w, g[v].y, acc.y);
+                        acc.z = fmaf(w, g[v].z, acc.z); acc.w = fmaf(w, g[v].w, acc.w);
+                    }
+                } else {
+#pragma unroll
+                    for (int v = 0; v < IB_MAXR; ++v)
+                        if (wx[v] != 0.f) acc.x = fmaf(wy * wx[v], a.in[o + (long long)v * cq], acc.x);
+                }
+            }
+            const long long e = (long long)row * rowlen + t;
+            if (VEC) reinterpret_cast<float4*>(a.out)[e] = acc;
+            else a.out[e] = acc.x;
+        }
+    }
+}
+
+// Forward with the same per-CTA x table (source columns and weight per output column) and per-row y weights: the per-thread
+// work is four float4 loads, the blend and one float4 store.
+template <bool VEC>
+__global__ void __launch_bounds__(256) interp_fwd_table_kernel(InterpArgs a) {
+    pdl_enter();
+    extern __shared__ __align__(16) float tab[];       // [Wout] lx, then [Wout] x0, [Wout] x1 (int)
+    float* lxs = tab;
+    int* x0s = reinterpret_cast<int*>(tab + a.Wout);
+    int* x1s = x0s + a.Wout;
+    for (int ox = threadIdx.x; ox < a.Wout; ox += blockDim.x) {
+        int x0, x1; float lx;
+        src_index(a.sx, ox, a.Win, x0, x1, lx);
+        lxs[ox] = lx; x0s[ox] = x0; x1s[ox] = x1;
+    }
+    __syncthreads();
+    const int cq = VEC ? a.C / 4 : a.C;
+    const int rowlen = a.Wout * cq;
+    for (int row = blockIdx.x; row < a.B * a.Hout; row += gridDim.x) {
+        const int b = row / a.Hout, oy = row % a.Hout;
+        int y0, y1; float ly;
+        src_index(a.sy, oy, a.Hin, y0, y1, ly);
+        const float hy = 1.f - ly;
+        const long long r0 = ((long long)b * a.Hin + y0) * a.Win, r1 = ((long long)b * a.Hin + y1) * a.Win;
+        for (int t = threadIdx.x; t < rowlen; t += blockDim.x) {
+            const int ox = t / cq, c = t % cq;
+            const int x0 = x0s[ox], x1 = x1s[ox];
+            const float lx = lxs[ox], hx = 1.f - lx;
+            const long long e = (long long)row * rowlen + t;
+            if (VEC) {
+                const float4* in4 = reinterpret_cast<const float4*>(a.in);
+                const float4 v00 = in4[(r0 + x0) * cq + c], v01 = in4[(r0 + x1) * cq + c];
+                const float4 v10 = in4[(r1 + x0) * cq + c], v11 = in4[(r1 + x1) * cq + c];
+                float4 o;
+                o.x = hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x);
+                o.y = hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
+                o.z = hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
+                o.w = hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
+                reinterpret_cast<float4*>(a.out)[e] = o;
+            } else {
+                const float v00 = a.in[(r0 + x0) * cq + c], v01 = a.in[(r0 + x1) * cq + c];
+                const float v10 = a.in[(r1 + x0) * cq + c], v11 = a.in[(r1 + x1) * cq + c];
+                a.out[e] = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+            }
+        }
+    }
+}
+
+// widest candidate range dst_range can return for this scale (host mirror of the device arithmetic, with slack)
+static int max_candidates(float scale, int nout) {
+    if (scale <= 0.f) return nout;
+    return (int)(2.0f / scale) + 4;
+}
+
 static int launch_interp(bool backward, const float* in, float* out, int B, int Hin, int Win, int Hout, int Wout, int C,
                          cudaStream_t st) {
     InterpArgs a;
@@ -157,11 +283,27 @@ static int launch_interp(bool backward, const float* in, float* out, int B, int 
     if (blocks > 148 * 32) blocks = 148 * 32;
     if (blocks < 1) blocks = 1;
     if (backward) {
-        if (vec) launch_pdl(interp_bwd_kernel<true>, (int)blocks, 256, 0, st, a);
-        else launch_pdl(interp_bwd_kernel<false>, (int)blocks, 256, 0, st, a);
+        static const int use_table = [] { const char* v = getenv("GB200_INTERP_TABLE"); return v ? atoi(v) : 1; }();
+        const size_t smem = (size_t)Win * (IB_MAXR + 1) * sizeof(float);
+        if (use_table && max_candidates(a.sy, Hout) <= IB_MAXR && max_candidates(a.sx, Wout) <= IB_MAXR && smem <= 40 * 1024) {
+            if (vec) launch_pdl(interp_bwd_table_kernel<true>, (int)blocks, 256, smem, st, a);
+            else launch_pdl(interp_bwd_table_kernel<false>, (int)blocks, 256, smem, st, a);
+        } else if (vec) {
+            launch_pdl(interp_bwd_kernel<true>, (int)blocks, 256, 0, st, a);
+        } else {
+            launch_pdl(interp_bwd_kernel<false>, (int)blocks, 256, 0, st, a);
+        }
     } else {
-        if (vec) launch_pdl(interp_fwd_kernel<true>, (int)blocks, 256, 0, st, a);
-        else launch_pdl(interp_fwd_kernel<false>, (int)blocks, 256, 0, st, a);
+        static const int use_table = [] { const char* v = getenv("GB200_INTERP_TABLE"); return v ? atoi(v) : 1; }();
+        const size_t smem = (size_t)Wout * 3 * sizeof(float);
+        if (use_table && smem <= 40 * 1024) {
+            if (vec) launch_pdl(interp_fwd_table_kernel<true>, (int)blocks, 256, smem, st, a);
+            else launch_pdl(interp_fwd_table_kernel<false>, (int)blocks, 256, smem, st, a);
+        } else if (vec) {
+            launch_pdl(interp_fwd_kernel<true>, (int)blocks, 256, 0, st, a);
+        } else {
+            launch_pdl(interp_fwd_kernel<false>, (int)blocks, 256, 0, st, a);
+        }
     }
     return check_launch(backward ? "gb200_interp_bilinear_bwd" : "gb200_interp_bilinear_fwd");
 }

@@ -404,23 +404,140 @@ __global__ void __launch_bounds__(128) ydft_row_kernel(const float* __restrict__
     }
 }
 
+// Channel-blocked forward transform: a thread owns 4 channels x YQ_KPT modes of one row and every YQ-th point of it, so each
+// twiddle word read from shared memory (a broadcast: 1 word per cycle, however wide the load) feeds 4 FMAs and each x
+// value (one float4 straight from global memory) feeds 2*YQ_KPT.  ncu showed the first version latency-bound (long-scoreboard
+// stalls at 23% occupancy): the point split is 8-way where the thread budget allows (twice the warps), the x loads are
+// double-buffered one batch ahead, and the twiddle table is filled with six independent loads per thread in flight.
+// The YQ point groups are reduced through shared memory in fixed order.
+constexpr int YQ_KPT = 6;
+constexpr int YQ_UN = 6;
+
+template <int YQ>
+__global__ void __launch_bounds__(128) ydft_rowq_kernel(const float* __restrict__ x, long long R, int n, int P, int C, int m,
+                                                        int CG, int KG, const float2* __restrict__ twY, float scale,
+                                                        int hermitian, float2* __restrict__ out) {
+    pdl_enter();
+    extern __shared__ __align__(16) float sm[];
+    constexpr int SLOTS = 128 / YQ;           // (row, cg, kg) slots per CTA
+    constexpr int ACC = 2 * YQ_KPT * 4;
+    float* twc = sm;                          // [KG*YQ_KPT][P]   rows >= m are zero
+    float* tws = twc + KG * YQ_KPT * P;
+    float* red = tws + KG * YQ_KPT * P;       // [YQ-1][SLOTS][ACC]
+    const int TPR = CG * KG;                  // threads per (row, point group): a power of two <= SLOTS
+    const int rows = SLOTS / TPR;
+    for (int k0 = 0; k0 < KG * YQ_KPT; k0 += YQ_KPT) {
+        for (int y = threadIdx.x; y < P; y += 128) {
+            float2 t[YQ_KPT];
+#pragma unroll
+            for (int j = 0; j < YQ_KPT; ++j)
+                t[j] = (k0 + j < m && y < n) ? twY[(long long)(k0 + j) * n + y] : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < YQ_KPT; ++j) {
+                twc[(k0 + j) * P + y] = t[j].x;
+                tws[(k0 + j) * P + y] = t[j].y;
+            }
+        }
+    }
+    __syncthreads();
+    const int slot = threadIdx.x / YQ;
+    const int yq = threadIdx.x % YQ;
+    const int rl = slot / TPR, cg = (slot % TPR) % CG, kg = (slot % TPR) / CG;
+    const long long row = (long long)blockIdx.x * rows + rl;
+    const bool live = row < R;
+    float are[YQ_KPT][4], aim[YQ_KPT][4];
+#pragma unroll
+    for (int k = 0; k < YQ_KPT; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { are[k][j] = 0.f; aim[k][j] = 0.f; }
+    const float* xp = x + (live ? row : 0) * n * C + 4 * cg;
+    const float* pc = twc + kg * YQ_KPT * P;
+    const float* ps = tws + kg * YQ_KPT * P;
+    constexpr int STEP = YQ * YQ_UN;
+    auto load = [&](float4 (&v)[YQ_UN], int y0) {
+#pragma unroll
+        for (int u = 0; u < YQ_UN; ++u) {
+            const int y = y0 + YQ * u;
+            v[u] = (live && y < n) ? *reinterpret_cast<const float4*>(xp + (long long)y * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto consume = [&](const float4 (&v)[YQ_UN], int y0) {
+#pragma unroll
+        for (int u = 0; u < YQ_UN; ++u) {
+            const int y = min(y0 + YQ * u, P - 1);          // v[u] is zero past the end of the row
+#pragma unroll
+            for (int k = 0; k < YQ_KPT; ++k) {
+                const float c = pc[k * P + y], sn = ps[k * P + y];
+                are[k][0] = fmaf(v[u].x, c, are[k][0]); aim[k][0] = fmaf(-v[u].x, sn, aim[k][0]);
+                are[k][1] = fmaf(v[u].y, c, are[k][1]); aim[k][1] = fmaf(-v[u].y, sn, aim[k][1]);
+                are[k][2] = fmaf(v[u].z, c, are[k][2]); aim[k][2] = fmaf(-v[u].z, sn, aim[k][2]);
+                are[k][3] = fmaf(v[u].w, c, are[k][3]); aim[k][3] = fmaf(-v[u].w, sn, aim[k][3]);
+            }
+        }
+    };
+    float4 va[YQ_UN], vb[YQ_UN];
+    load(va, yq);
+    for (int y0 = yq; y0 < n; y0 += 2 * STEP) {
+        load(vb, y0 + STEP);                 // next batch in flight while this one is consumed (zero past the end)
+        consume(va, y0);
+        if (y0 + STEP < n) {
+            load(va, y0 + 2 * STEP);
+            consume(vb, y0 + STEP);
+        }
+    }
+    if (yq > 0) {
+        float* r = red + ((yq - 1) * SLOTS + slot) * ACC;
+#pragma unroll
+        for (int k = 0; k < YQ_KPT; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { r[k * 8 + j] = are[k][j]; r[k * 8 + 4 + j] = aim[k][j]; }
+    }
+    __syncthreads();
+    if (yq == 0 && live) {
+#pragma unroll 1
+        for (int q = 0; q < YQ - 1; ++q) {
+            const float* r = red + (q * SLOTS + slot) * ACC;
+#pragma unroll
+            for (int k = 0; k < YQ_KPT; ++k)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { are[k][j] += r[k * 8 + j]; aim[k][j] += r[k * 8 + 4 + j]; }
+        }
+#pragma unroll
+        for (int k = 0; k < YQ_KPT; ++k) {
+            const int ky = kg * YQ_KPT + k;
+            if (ky < m) {
+                const float sc = scale * (hermitian ? herm_weight(ky, n) : 1.f);
+                float4* o = reinterpret_cast<float4*>(out + (row * m + ky) * C + 4 * cg);
+                o[0] = make_float4(are[k][0] * sc, aim[k][0] * sc, are[k][1] * sc, aim[k][1] * sc);
+                o[1] = make_float4(are[k][2] * sc, aim[k][2] * sc, are[k][3] * sc, aim[k][3] * sc);
+            }
+        }
+    }
+}
+
 constexpr int XD_RG = 6;    // modes kx per CTA
 
-__global__ void __launch_bounds__(128) xdft_rows_kernel(const float2* __restrict__ T1, int n, int m, int C,
-                                                        const float2* __restrict__ twX, float scale,
-                                                        float2* __restrict__ out) {
+constexpr int XD_XQ = 8;    // thread groups splitting X (one warp each)
+
+__global__ void __launch_bounds__(32 * XD_XQ) xdft_rows_kernel(const float2* __restrict__ T1, int n, int m, int C,
+                                                               const float2* __restrict__ twX, float scale,
+                                                               float2* __restrict__ out) {
     pdl_enter();
-    __shared__ float2 red[3][XD_RG][32];
+    __shared__ float2 red[XD_XQ - 1][XD_RG][32];
     extern __shared__ __align__(16) float2 tw2[];          // [XD_RG][n]
     const int r0 = blockIdx.x * XD_RG, ky = blockIdx.y, b = blockIdx.z;
     const int nr = min(XD_RG, 2 * m - r0);
-    for (int e = threadIdx.x; e < XD_RG * n; e += 128) {
-        const int j = e / n, X = e % n;
-        tw2[e] = j < nr ? twX[(long long)(r0 + j) * n + X] : make_float2(0.f, 0.f);
+    for (int X = threadIdx.x; X < n; X += blockDim.x) {
+        float2 t[XD_RG];
+#pragma unroll
+        for (int j = 0; j < XD_RG; ++j) t[j] = j < nr ? twX[(long long)(r0 + j) * n + X] : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < XD_RG; ++j) tw2[j * n + X] = t[j];
     }
     __syncthreads();
     const int cl = threadIdx.x % 32, xq = threadIdx.x / 32;
     const long long xstride = (long long)m * C;
+    constexpr int STEP = 4 * XD_XQ;
     for (int c0 = 0; c0 < C; c0 += 32) {
         const int c = c0 + cl;
         const bool cok = c < C;
@@ -428,22 +545,33 @@ __global__ void __launch_bounds__(128) xdft_rows_kernel(const float2* __restrict
 #pragma unroll
         for (int j = 0; j < XD_RG; ++j) { are[j] = 0.f; aim[j] = 0.f; }
         const float2* tp = T1 + (((long long)b * n) * m + ky) * C + (cok ? c : 0);
-        for (int X0 = xq; X0 < n; X0 += 16) {
-            float2 t[4];
+        auto load = [&](float2 (&t)[4], int X0) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int X = X0 + 4 * u;
+                const int X = X0 + XD_XQ * u;
                 t[u] = (cok && X < n) ? tp[X * xstride] : make_float2(0.f, 0.f);
             }
+        };
+        auto consume = [&](const float2 (&t)[4], int X0) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int X = min(X0 + 4 * u, n - 1);          // t[u] is zero past the end
+                const int X = min(X0 + XD_XQ * u, n - 1);          // t[u] is zero past the end
 #pragma unroll
                 for (int j = 0; j < XD_RG; ++j) {
                     const float2 w = tw2[j * n + X];
                     are[j] = fmaf(t[u].x, w.x, fmaf(t[u].y, w.y, are[j]));
                     aim[j] = fmaf(t[u].y, w.x, fmaf(-t[u].x, w.y, aim[j]));
                 }
+            }
+        };
+        float2 ta[4], tb[4];
+        load(ta, xq);
+        for (int X0 = xq; X0 < n; X0 += 2 * STEP) {
+            load(tb, X0 + STEP);
+            consume(ta, X0);
+            if (X0 + STEP < n) {
+                load(ta, X0 + 2 * STEP);
+                consume(tb, X0 + STEP);
             }
         }
         if (xq > 0) {
@@ -457,7 +585,7 @@ __global__ void __launch_bounds__(128) xdft_rows_kernel(const float2* __restrict
                 if (j < nr) {
                     float sr = are[j], si = aim[j];
 #pragma unroll
-                    for (int q = 0; q < 3; ++q) { sr += red[q][j][cl].x; si += red[q][j][cl].y; }
+                    for (int q = 0; q < XD_XQ - 1; ++q) { sr += red[q][j][cl].x; si += red[q][j][cl].y; }
                     out[(((long long)b * 2 * m + r0 + j) * m + ky) * C + c] = make_float2(sr * scale, si * scale);
                 }
             }
@@ -663,6 +791,29 @@ extern "C" int gb200_spectral_ydft(int device, const float* x, long long R, int 
 #undef YD
         return check_launch("gb200_spectral_ydft");
     }
+    if (spectral_rows_enabled() && nsplit == 1 && C % 4 == 0 && R >= 148 && R <= 0x7fffffffLL && aligned16(x) &&
+        aligned16(out)) {
+        const int CG = C / 4, KG = cdiv(m, YQ_KPT), TPR = CG * KG;
+        const int P = n | 1;                              // odd pitch: the KG mode groups of a warp fall in distinct banks
+        static const int yq_env = [] { const char* v = getenv("GB200_YDFT_YQ"); return v ? atoi(v) : 4; }();
+        const int YQ = (yq_env == 8 && TPR <= 16) ? 8 : 4;   // point split (8-way needs the row to fit the 128-thread CTA)
+        const size_t smem = (size_t)(2 * KG * YQ_KPT * P + (YQ - 1) * (128 / YQ) * 2 * YQ_KPT * 4) * sizeof(float);
+        if (yq_env != 0 && TPR <= 32 && (TPR & (TPR - 1)) == 0 && smem <= 96 * 1024) {
+            const int rows = (128 / YQ) / TPR;
+            if (YQ == 8) {
+                if (smem > 48 * 1024)
+                    cudaFuncSetAttribute(ydft_rowq_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                launch_pdl(ydft_rowq_kernel<8>, dim3((unsigned)cdiv(R, rows)), 128, smem, st, x, R, n, P, C, m, CG, KG,
+                           reinterpret_cast<const float2*>(twY), scale, hermitian, reinterpret_cast<float2*>(out));
+            } else {
+                if (smem > 48 * 1024)
+                    cudaFuncSetAttribute(ydft_rowq_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                launch_pdl(ydft_rowq_kernel<4>, dim3((unsigned)cdiv(R, rows)), 128, smem, st, x, R, n, P, C, m, CG, KG,
+                           reinterpret_cast<const float2*>(twY), scale, hermitian, reinterpret_cast<float2*>(out));
+            }
+            return check_launch("gb200_spectral_ydft");
+        }
+    }
     {
         const int NP = (n + 3) / 4 * 4;
         const size_t smem = (size_t)(NP * C + 2 * m * NP) * sizeof(float);
@@ -703,7 +854,7 @@ extern "C" int gb200_spectral_xdft(int device, const float* T1, int B, int n, in
         if (!inverse) {
             const size_t smem = (size_t)XD_RG * n * sizeof(float2);
             if (smem <= 40 * 1024) {
-                launch_pdl(xdft_rows_kernel, dim3(cdiv(2 * m, XD_RG), m, B), 128, smem, st,
+                launch_pdl(xdft_rows_kernel, dim3(cdiv(2 * m, XD_RG), m, B), 32 * XD_XQ, smem, st,
                            reinterpret_cast<const float2*>(T1), n, m, C, reinterpret_cast<const float2*>(twX), scale,
                            reinterpret_cast<float2*>(out));
                 return check_launch("gb200_spectral_xdft");
