@@ -304,6 +304,49 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(Conv1Args a) {
     }
 }
 
+// Row-structured variant (C <= 128): CTA = one image row, the three input rows it needs sit zero-padded in shared memory,
+// a thread keeps the nine taps of its four channels in registers and walks the row eight pixels apart.  The grid-stride
+// kernel above spent its time on 64-bit index arithmetic and per-tap bounds tests (83 us for an 81 MB output).
+__global__ void __launch_bounds__(256) conv1_fwd_row_kernel(Conv1Args a) {
+    extern __shared__ float xs[];                               // [3][W + 2]
+    const int W = a.W, WP = W + 2;
+    const int cq = threadIdx.x & 31, ph = threadIdx.x >> 5, c = cq * 4;
+    const bool cok = c < a.C;
+    float4 wr[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+        wr[t] = cok ? make_float4(a.w[(c + 0) * 9 + t], a.w[(c + 1) * 9 + t], a.w[(c + 2) * 9 + t], a.w[(c + 3) * 9 + t])
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+    const unsigned long long so = (a.p > 0.f && a.seed_off) ? *a.seed_off : 0ull;
+    for (int row = blockIdx.x; row < a.B * a.H; row += gridDim.x) {
+        const int b = row / a.H, yy = row % a.H;
+        __syncthreads();
+        for (int i = threadIdx.x; i < 3 * WP; i += blockDim.x) {
+            const int r = i / WP, xx = i % WP - 1, y2 = yy + r - 1;
+            xs[i] = (y2 >= 0 && y2 < a.H && xx >= 0 && xx < W) ? a.x[((long long)b * a.H + y2) * W + xx] : 0.f;
+        }
+        __syncthreads();
+        if (!cok) continue;
+        for (int xx = ph; xx < W; xx += 8) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const float xv = xs[(t / 3) * WP + xx + t % 3];
+                acc.x = fmaf(xv, wr[t].x, acc.x); acc.y = fmaf(xv, wr[t].y, acc.y);
+                acc.z = fmaf(xv, wr[t].z, acc.z); acc.w = fmaf(xv, wr[t].w, acc.w);
+            }
+            const long long px = (long long)row * W + xx;
+            if (a.p > 0.f) {
+                const float4 ds = dropout_scale4(a.p, a.seed + so, (unsigned long long)px * a.C + c);
+                acc.x *= ds.x; acc.y *= ds.y; acc.z *= ds.z; acc.w *= ds.w;
+            }
+            acc.x = act_apply(a.act, acc.x); acc.y = act_apply(a.act, acc.y);
+            acc.z = act_apply(a.act, acc.z); acc.w = act_apply(a.act, acc.w);
+            *reinterpret_cast<float4*>(a.y + px * a.C + c) = acc;
+        }
+    }
+}
+
 // g = dy * act'(y) * mask (ReLU only: y > 0 <=> kept and positive), then
 //   dx[px]        = sum_{tap, c} g[px - tap][c] w[c][tap]                     (one warp per pixel)
 //   dw[c][tap]    = sum_px g[px][c] x[px + tap]                                (thread = channel, CTA = pixel range)
@@ -377,6 +420,67 @@ __global__ void __launch_bounds__(256) conv1_wgrad_kernel(Conv1BwdArgs a) {
     for (int t = 0; t < 9; ++t)
 #pragma unroll
         for (int i = 0; i < 4; ++i) red[ph][t][c + i] = acc[t][i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * a.C; i += blockDim.x) {
+        const int t = i / a.C, cc = i % a.C;
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[k][t][cc];
+        a.dwpart[((long long)blockIdx.x * 9 + t) * a.C + cc] = s;
+    }
+}
+
+// Row-structured weight gradient: CTA = `rows_per_cta` consecutive image rows, input rows staged in shared memory, two
+// pixels (four float4 loads) in flight per thread, no 64-bit index arithmetic in the loop.
+__global__ void __launch_bounds__(256) conv1_wgrad_row_kernel(Conv1BwdArgs a, int rows_per_cta) {
+    __shared__ float red[8][9][128 + 4];
+    extern __shared__ float xs[];                               // [3][W + 2]
+    const int W = a.W, WP = W + 2;
+    const int cq = threadIdx.x & 31, ph = threadIdx.x >> 5, c = cq * 4;
+    const bool cok = c < a.C;
+    float acc[9][4];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < rows_per_cta; ++r) {
+        const int row = blockIdx.x * rows_per_cta + r;
+        if (row >= a.B * a.H) break;
+        const int b = row / a.H, yy = row % a.H;
+        __syncthreads();
+        for (int i = threadIdx.x; i < 3 * WP; i += blockDim.x) {
+            const int rr = i / WP, xx = i % WP - 1, y2 = yy + rr - 1;
+            xs[i] = (y2 >= 0 && y2 < a.H && xx >= 0 && xx < W) ? a.x[((long long)b * a.H + y2) * W + xx] : 0.f;
+        }
+        __syncthreads();
+        if (!cok) continue;
+        const float* yrow = a.y + (long long)row * W * a.C + c;
+        const float* grow = a.dy + (long long)row * W * a.C + c;
+        for (int xx = ph; xx < W; xx += 16) {
+            const bool two = xx + 8 < W;
+            const float4 y0 = *reinterpret_cast<const float4*>(yrow + (long long)xx * a.C);
+            float4 g0 = *reinterpret_cast<const float4*>(grow + (long long)xx * a.C);
+            const float4 y1 = two ? *reinterpret_cast<const float4*>(yrow + (long long)(xx + 8) * a.C) : zero4;
+            float4 g1 = two ? *reinterpret_cast<const float4*>(grow + (long long)(xx + 8) * a.C) : zero4;
+            g0.x = y0.x > 0.f ? g0.x * a.keep : 0.f; g0.y = y0.y > 0.f ? g0.y * a.keep : 0.f;
+            g0.z = y0.z > 0.f ? g0.z * a.keep : 0.f; g0.w = y0.w > 0.f ? g0.w * a.keep : 0.f;
+            g1.x = y1.x > 0.f ? g1.x * a.keep : 0.f; g1.y = y1.y > 0.f ? g1.y * a.keep : 0.f;
+            g1.z = y1.z > 0.f ? g1.z * a.keep : 0.f; g1.w = y1.w > 0.f ? g1.w * a.keep : 0.f;
+            const int x1 = two ? xx + 8 : xx;                     // g1 is zero when there is no second pixel
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const float xv0 = xs[(t / 3) * WP + xx + t % 3], xv1 = xs[(t / 3) * WP + x1 + t % 3];
+                acc[t][0] = fmaf(g1.x, xv1, fmaf(g0.x, xv0, acc[t][0])); acc[t][1] = fmaf(g1.y, xv1, fmaf(g0.y, xv0, acc[t][1]));
+                acc[t][2] = fmaf(g1.z, xv1, fmaf(g0.z, xv0, acc[t][2])); acc[t][3] = fmaf(g1.w, xv1, fmaf(g0.w, xv0, acc[t][3]));
+            }
+        }
+    }
+    __syncthreads();
+    if (cok) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) red[ph][t][c + i] = acc[t][i];
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < 9 * a.C; i += blockDim.x) {
         const int t = i / a.C, cc = i % a.C;
@@ -482,6 +586,13 @@ extern "C" int gb200_conv1_fwd(int device, const float* x, const float* w, float
     const long long total = (long long)B * H * W * (C / 4);
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
+    static const int rows_on = [] { const char* v = getenv("GB200_CONV1_ROWS"); return v ? atoi(v) : 1; }();
+    if (rows_on && C <= 128 && W <= 4096) {
+        int rb = B * H;
+        if (rb > 148 * 16) rb = 148 * 16;
+        conv1_fwd_row_kernel<<<rb, 256, 3 * (W + 2) * sizeof(float), as_stream(stream)>>>(a);
+        return check_launch("gb200_conv1_fwd");
+    }
     conv1_fwd_kernel<<<blocks, 256, 9 * C * sizeof(float), as_stream(stream)>>>(a);
     return check_launch("gb200_conv1_fwd");
 }
@@ -503,8 +614,16 @@ extern "C" int gb200_conv1_bwd(int device, const float* dy, const float* y, cons
         conv1_dgrad_kernel<<<148 * 8, 256, 9 * C * sizeof(float), st>>>(a);
         ++launched;
     }
-    const int nparts = 148 * 4;
-    conv1_wgrad_kernel<<<nparts, 256, 0, st>>>(a);
+    int nparts = 148 * 4;
+    static const int rows_on = [] { const char* v = getenv("GB200_CONV1_ROWS"); return v ? atoi(v) : 1; }();
+    if (rows_on && W <= 512) {
+        const int nrows = B * H;
+        const int rpc = (nrows + nparts - 1) / nparts;          // the workspace holds 148 * 4 partials
+        nparts = (nrows + rpc - 1) / rpc;
+        conv1_wgrad_row_kernel<<<nparts, 256, 3 * (W + 2) * sizeof(float), st>>>(a, rpc);
+    } else {
+        conv1_wgrad_kernel<<<nparts, 256, 0, st>>>(a);
+    }
     conv1_wgrad_final_kernel<<<(9 * C + 127) / 128, 128, 0, st>>>(workspace, nparts, C, dw);
     return check_launch("gb200_conv1_bwd", launched);
 }
