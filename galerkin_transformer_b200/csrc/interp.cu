@@ -156,7 +156,7 @@ constexpr int IB_MAXR = 8;
 template <bool VEC>
 __global__ void __launch_bounds__(256) interp_bwd_table_kernel(InterpArgs a) {
     pdl_enter();
-    extern __shared__ __align__(16) float tab[];       // [Win][IB_MAXR] weights, then [Win] first candidate column (int)
+    extern __shared__ __align__(16) float tab[];       // [Win][IB_MAXR] weights from the first live column on, then [Win] that column
     __shared__ float s_wy[IB_MAXR];
     __shared__ int s_ylo;
     float* wxs = tab;
@@ -164,9 +164,23 @@ __global__ void __launch_bounds__(256) interp_bwd_table_kernel(InterpArgs a) {
     for (int ix = threadIdx.x; ix < a.Win; ix += blockDim.x) {
         int xlo, xhi;
         dst_range(a.sx, ix, a.Wout, xlo, xhi);
-        xlos[ix] = xlo;
+        float w[IB_MAXR];
+        int first = IB_MAXR;
 #pragma unroll
-        for (int v = 0; v < IB_MAXR; ++v) wxs[ix * IB_MAXR + v] = (xlo + v <= xhi) ? axis_weight(a.sx, xlo + v, a.Win, ix) : 0.f;
+        for (int v = IB_MAXR - 1; v >= 0; --v) {
+            w[v] = (xlo + v <= xhi) ? axis_weight(a.sx, xlo + v, a.Win, ix) : 0.f;
+            if (w[v] != 0.f) first = v;
+        }
+        if (first == IB_MAXR) first = 0;
+        xlos[ix] = xlo + first;                        // live taps are contiguous: shift them to the front
+#pragma unroll
+        for (int v = 0; v < IB_MAXR; ++v) {
+            float t = 0.f;
+#pragma unroll
+            for (int q = 0; q < IB_MAXR; ++q)
+                if (q == v + first) t = w[q];
+            wxs[ix * IB_MAXR + v] = t;
+        }
     }
     const int cq = VEC ? a.C / 4 : a.C;
     const int rowlen = a.Win * cq;
@@ -185,9 +199,10 @@ __global__ void __launch_bounds__(256) interp_bwd_table_kernel(InterpArgs a) {
         for (int t = threadIdx.x; t < rowlen; t += blockDim.x) {
             const int ix = t / cq, c = t % cq;
             const int xlo = xlos[ix];
-            float wx[IB_MAXR];
-#pragma unroll
-            for (int v = 0; v < IB_MAXR; ++v) wx[v] = wxs[ix * IB_MAXR + v];
+            const float4 wa = *reinterpret_cast<const float4*>(wxs + ix * IB_MAXR);
+            const float4 wb = *reinterpret_cast<const float4*>(wxs + ix * IB_MAXR + 4);
+            const float wx[IB_MAXR] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+            const bool tail = wb.x != 0.f;                             // more than four live columns (ratios above ~2x)
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
             for (int u = 0; u < IB_MAXR; ++u) {
@@ -195,16 +210,27 @@ __global__ void __launch_bounds__(256) interp_bwd_table_kernel(InterpArgs a) {
                 if (wy == 0.f) continue;                               // uniform over the CTA
                 const long long o = (base + (long long)(ylo + u) * a.Wout + xlo) * cq + c;
                 if (VEC) {
-                    float4 g[IB_MAXR];
+                    float4 g[4];
 #pragma unroll
-                    for (int v = 0; v < IB_MAXR; ++v)
+                    for (int v = 0; v < 4; ++v)
                         g[v] = wx[v] != 0.f ? reinterpret_cast<const float4*>(a.in)[o + (long long)v * cq]
                                             : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int v = 0; v < IB_MAXR; ++v) {
+                    for (int v = 0; v < 4; ++v) {
                         const float w = wy * wx[v];
                         acc.x = fmaf(w, g[v].x, acc.x); acc.y = fmaf(w, g[v].y, acc.y);
                         acc.z = fmaf(w, g[v].z, acc.z); acc.w = fmaf(w, g[v].w, acc.w);
+                    }
+                    if (tail) {
+#pragma unroll
+                        for (int v = 4; v < IB_MAXR; ++v) {
+                            if (wx[v] != 0.f) {
+                                const float4 gg = reinterpret_cast<const float4*>(a.in)[o + (long long)v * cq];
+                                const float w = wy * wx[v];
+                                acc.x = fmaf(w, gg.x, acc.x); acc.y = fmaf(w, gg.y, acc.y);
+                                acc.z = fmaf(w, gg.z, acc.z); acc.w = fmaf(w, gg.w, acc.w);
+                            }
+                        }
                     }
                 } else {
 #pragma unroll

@@ -281,10 +281,15 @@ def gemm(A, B, C, M, N, K, *, lda, ldb, ldc, transA=False, transB=False, alpha=1
             drop_p, seed, ptr(residual), ldr, rscale, int(accumulate), ksplit, ptr(ws), ws_bytes, stream_of(C))
 
 
+_DIAG_SKIP_WGRAD = os.environ.get("GB200_DIAG_SKIP_WGRAD", "0") == "1"
+
+
 def wgrad_group(problems, T):
     """[(G (T, M) view, M, ldg, X (T, N), N, dW (M, N)), ...] (at most 6): dW = G^T X for each, one tcgen05 TF32 split-K launch
     and one deterministic reduction for the whole group (gb200_gemm_tc_wgrad_group)."""
     lib = _lib.load()
+    if _DIAG_SKIP_WGRAD:          # timing diagnostics only (tools/): the gradients are then garbage
+        return
     n = len(problems)
     arr = (_lib.WgradProblem * n)()
     flops = nbytes = 0.0
