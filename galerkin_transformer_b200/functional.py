@@ -160,6 +160,12 @@ def set_backward_streams(on):
     _BWD_STREAMS = bool(on)
 
 
+def _weak(t):
+    """weak reference to an optional parameter tensor (autograd contexts must not keep non-saved tensors alive)"""
+    import weakref
+    return (lambda: None) if t is None else weakref.ref(t)
+
+
 class _Fork:
     """`with fork.side(i):` enqueues on side stream i (which first waits, on every entry, for everything enqueued on
     the launching stream so far); `join()` makes the launching stream wait for the side work.  Outputs must be allocated BEFORE
@@ -220,6 +226,7 @@ def aux_stream(device):
 
 _pending_joins = []
 _join_queued = False
+_DEFER_WGRAD_JOIN = os.environ.get("GB200_DEFER_WGRAD_JOIN", "1") != "0"
 
 
 def _join_pending():
@@ -231,6 +238,45 @@ def _join_pending():
     for main, streams, _keep in items:
         for st in streams:
             main.wait_stream(st)
+
+
+def _note_use(*params):
+    """Forward bookkeeping for _finish_fork: how many autograd nodes of the graph being built use each parameter."""
+    if not torch.is_grad_enabled():
+        return
+    for p in params:
+        if p is not None and p.requires_grad:
+            p._gb200_pending = getattr(p, "_gb200_pending", 0) + 1
+            p._gb200_total = getattr(p, "_gb200_total", 0) + 1
+
+
+def _single_use(params):
+    """Backward: True when every parameter feeds exactly ONE node of this graph and has no gradient yet -- only then does
+    autograd adopt the gradient tensor as it is.  A parameter used several times (a rollout applying the model repeatedly) or
+    with an existing .grad is summed by the engine on the launching stream, which must then see finished side-stream work."""
+    ok = True
+    for p in params:
+        if p is None:
+            continue
+        if not p.is_leaf or getattr(p, "_gb200_total", 1) > 1 or p.grad is not None:
+            ok = False          # (a non-leaf "parameter", e.g. a packed weight, is consumed by the next node right away)
+        pend = getattr(p, "_gb200_pending", 1) - 1
+        p._gb200_pending = max(pend, 0)
+        if pend <= 0:
+            p._gb200_total = 0
+    return ok
+
+
+def _finish_fork(fork, params, keepalive):
+    """End of a backward node whose parameter gradients were launched on side streams: normally the launching stream joins
+    them only when the whole backward pass has been enqueued (they then overlap every later node instead of the rest of
+    this one).  That needs autograd to ADOPT the gradient tensors (`p.grad is None`: no accumulation kernel on the
+    launching stream before the side stream has written them) -- otherwise, or with GB200_DEFER_WGRAD_JOIN=0, join now.
+    `keepalive`: the tensors the side work reads (not its outputs: a second reference would make autograd copy them)."""
+    if _single_use(params) and _DEFER_WGRAD_JOIN:
+        fork.join_at_end_of_backward(keepalive)
+    else:
+        fork.join()
 
 
 # ------------------------------------------------------------------------------------------
@@ -378,6 +424,7 @@ class _LinearFn(torch.autograd.Function):
              drop_p=drop_p, seed=seed, residual=residual, ldr=N, rscale=rscale)
         ctx.save_for_backward(x, weight, z, y if (act == ACT["relu"] and z is None) else None)
         ctx.cfg = (act, rscale, drop_p, seed, bias is not None, residual is not None)
+        ctx.bias_ref = _weak(bias)
         return y
 
     @staticmethod
@@ -416,7 +463,7 @@ class _LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             gemm(g, weight, dx, M, K, N, lda=N, ldb=K, ldc=K)
-        fork.join()
+        _finish_fork(fork, (weight, ctx.bias_ref()), (g, x))
         dres = dy if (has_res and ctx.needs_input_grad[3]) else None
         return dx, dw, db, dres, None, None, None, None
 
@@ -446,6 +493,7 @@ class _MLP2Fn(torch.autograd.Function):
              residual=x if shortcut else None, ldr=K, rscale=rscale)
         ctx.save_for_backward(x, w1, w2, h, z1)
         ctx.cfg = (act, p1, seed1, p2, seed2, rscale, shortcut, b1 is not None, b2 is not None)
+        ctx.bias_refs = (_weak(b1), _weak(b2))
         return y
 
     @staticmethod
@@ -502,7 +550,7 @@ class _MLP2Fn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             gemm(g1, w1, dx, M, K, N1, lda=N1, ldb=K, ldc=K, residual=dy if shortcut else None, ldr=N2)
-        fork.join()
+        _finish_fork(fork, (w1, w2, ctx.bias_refs[0](), ctx.bias_refs[1]()), (dy, g2, g1, h, x))
         return dx, dw1, db1, dw2, db2, None, None, None, None, None, None, None
 
 
@@ -514,6 +562,7 @@ def mlp2(x, w1, b1, w2, b2, *, act="relu", drop_p1=0.0, drop_p2=0.0, rscale=1.0,
         assert w2.shape[0] == x2.shape[1]
     seed1 = next_seed() if drop_p1 > 0.0 else 0
     seed2 = next_seed() if drop_p2 > 0.0 else 0
+    _note_use(w1, w2, b1, b2)
     y = _MLP2Fn.apply(x2, w1, b1, w2, b2, ACT[act], float(drop_p1), seed1, float(drop_p2), seed2, float(rscale),
                       bool(shortcut))
     return y.reshape(*lead, w2.shape[0])
@@ -525,6 +574,7 @@ def linear(x, weight, bias=None, *, act="none", residual=None, rscale=1.0, drop_
     x2 = x.reshape(-1, x.shape[-1]).contiguous()
     r2 = None if residual is None else residual.reshape(-1, weight.shape[0]).contiguous()
     seed = next_seed() if drop_p > 0.0 else 0
+    _note_use(weight, bias)
     y = _LinearFn.apply(x2, weight, bias, r2, ACT[act], float(rscale), float(drop_p), seed)
     return y.reshape(*lead, weight.shape[0])
 
@@ -549,6 +599,7 @@ class _LinearCatFn(torch.autograd.Function):
         gemm(x2, w2, y, M, N, K2, lda=K2, ldb=K2, ldc=N, transB=True, accumulate=True)
         ctx.save_for_backward(x1, x2, w1, w2)
         ctx.has_bias = bias is not None
+        ctx.weight_ref, ctx.bias_ref = _weak(weight), _weak(bias)
         return y
 
     @staticmethod
@@ -563,9 +614,11 @@ class _LinearCatFn(torch.autograd.Function):
         if ctx.needs_input_grad[2]:
             dw1 = torch.empty_like(w1)
             dw2 = torch.empty_like(w2)
+            dw = torch.empty((N, K1 + K2), dtype=torch.float32, device=dy.device)
             with fork.side(0):
                 gemm(dy, x1, dw1, N, K1, M, lda=N, ldb=K1, ldc=K1, transA=True, wgrad=True)
                 gemm(dy, x2, dw2, N, K2, M, lda=N, ldb=K2, ldc=K2, transA=True, wgrad=True)
+                torch.cat([dw1, dw2], dim=1, out=dw)
         if ctx.has_bias and ctx.needs_input_grad[3]:
             db = torch.empty(N, dtype=torch.float32, device=dy.device)
             with fork.side(1):
@@ -576,14 +629,13 @@ class _LinearCatFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dx2 = torch.empty_like(x2)
             gemm(dy, w2, dx2, M, K2, N, lda=N, ldb=K2, ldc=K2)
-        fork.join()
-        if dw1 is not None:
-            dw = torch.cat([dw1, dw2], dim=1)
+        _finish_fork(fork, (ctx.weight_ref(), ctx.bias_ref()), (dy, x1, x2, dw1, dw2))
         return dx1, dx2, dw, db
 
 
 def linear_cat(x1, x2, weight, bias=None):
     lead = x1.shape[:-1]
+    _note_use(weight, bias)
     y = _LinearCatFn.apply(x1.reshape(-1, x1.shape[-1]).contiguous(),
                            x2.reshape(-1, x2.shape[-1]).contiguous(), weight, bias)
     return y.reshape(*lead, weight.shape[0])
@@ -688,12 +740,14 @@ class _Conv3x3BlockFn(torch.autograd.Function):
                 npix, ptr(ghi), ptr(glo), ptr(yz), Cout, 0, act, p, seed, ptr(g), st)
         fork = _Fork(dy)
         if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(w)          # the parameter's own layout: autograd adopts it without a copy on this stream
             with fork.side(0):
                 prev = torch.backends.cudnn.allow_tf32
                 torch.backends.cudnn.allow_tf32 = True
                 try:
-                    dw = torch.ops.aten.convolution_backward(g.permute(0, 3, 1, 2), x.permute(0, 3, 1, 2), weight, None, [1, 1],
-                                                             [1, 1], [1, 1], False, [0, 0], 1, [False, True, False])[1]
+                    dw.copy_(torch.ops.aten.convolution_backward(g.permute(0, 3, 1, 2), x.permute(0, 3, 1, 2), weight, None,
+                                                                 [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
+                                                                 [False, True, False])[1])
                 finally:
                     torch.backends.cudnn.allow_tf32 = prev
         if ctx.needs_input_grad[0]:
@@ -702,7 +756,7 @@ class _Conv3x3BlockFn(torch.autograd.Function):
             dx = torch.empty_like(x)
             _launch("conv3x3_tc", 18.0 * npix * Cin * Cout, 4.0 * npix * (CPo + Cin) + wt.numel(), lib.gb200_conv3x3, dev,
                     ptr(ghi), ptr(glo), Cout, ptr(wt), Cin, B, H, W, ptr(dx), Cin, 0, None, None, 0, 0, 0, 0.0, 0, st)
-        fork.join()
+        _finish_fork(fork, (weight,), (g, x))
         return dx, dw, None, None, None
 
 
@@ -713,6 +767,7 @@ def conv3x3_supported(cin, cout):
 def conv3x3_block(x, weight, *, act="relu", drop_p=0.0):
     """x (B, H, W, Cin) channel-last -> act(dropout(conv3x3(x))) (B, H, W, Cout)"""
     seed = next_seed() if drop_p > 0.0 else 0
+    _note_use(weight)
     return _Conv3x3BlockFn.apply(x.contiguous(), weight, ACT[act], float(drop_p), seed)
 
 
@@ -988,7 +1043,7 @@ _FUSED_BACKWARD = os.environ.get("GB200_FUSED_BACKWARD", "1") != "0"     # A/B s
 # callback), so the grouped weight-gradient GEMM of layer l overlaps the input-gradient chain of layers l-1, l-2, ...
 # Measured at C3 with the grouped launch: 4.82 -> 4.67 ms/step.  GB200_DEFER_WGRAD_JOIN=0 joins per layer (graphs.GraphedStep does
 # that itself for concurrent micro-batch chains, whose per-chain streams are joined before the backward pass ends).
-_DEFER_WGRAD_JOIN = os.environ.get("GB200_DEFER_WGRAD_JOIN", "1") != "0"
+# (_DEFER_WGRAD_JOIN is defined next to _Fork)
 
 
 class _Ctx:
@@ -1167,10 +1222,7 @@ class _EncoderLayerFn(torch.autograd.Function):
                          (dqkv, dm, 3 * dm, x2d, dm, dwq), (dqkv[:, dm:], dm, 3 * dm, x2d, dm, dwk),
                          (dqkv[:, 2 * dm:], dm, 3 * dm, x2d, dm, dwv)], T)
         stage(16, 0.0, 0.0)
-        if _DEFER_WGRAD_JOIN:
-            fork.join_at_end_of_backward((dy2, g2, g1, dx1, gfc, dqkv, hid, x1, heads, x))
-        else:
-            fork.join()
+        _finish_fork(fork, params, (dy2, g2, g1, dx1, gfc, dqkv, hid, x1, heads, x))
         grads = [dwq, dwk, dwv] + [dvec[i * dm:(i + 1) * dm] for i in range(3)]
         o = 3 * dm
         if has_norm:
@@ -1188,6 +1240,7 @@ def encoder_layer(x, pos, params, *, n_head, pos_dim, eps, attention_scale, keep
            next_seed() if mask_p > 0.0 else 0, float(p_attn_out), next_seed() if p_attn_out > 0.0 else 0,
            float(res_sign), float(p_ffn), next_seed() if p_ffn > 0.0 else 0, float(p_out),
            next_seed() if p_out > 0.0 else 0)
+    _note_use(*params)
     return _EncoderLayerFn.apply(x.contiguous(), pos.contiguous(), keep_mask, cfg, packed, *params)
 
 
@@ -1295,6 +1348,7 @@ class _SpectralConvFn(torch.autograd.Function):
             y, z = _yidft_epi(Of, B, n, m, Co, twY, 1.0 / math.sqrt(n), True, x, Ci, wm, bl, act, need_z)
         ctx.save_for_backward(x, wl, fw0, fw1, Xf, z)
         ctx.cfg = (m, act, two_d, bl is not None, same)
+        ctx.bias_ref = _weak(bl)
         ctx.mark_non_differentiable(Of)
         return y, Of
 
@@ -1367,11 +1421,12 @@ class _SpectralConvFn(torch.autograd.Function):
                 dxf = dx
                 dx = torch.empty_like(x)
                 gemm(gz, wl, dx, P, Ci, Co, lda=Co, ldb=Ci, ldc=Ci)
-        fork.join()
+        _finish_fork(fork, (wl, fw0, fw1, ctx.bias_ref()), (gz, x, Xf, dO))
         return dx, dxf, dwl, dbl, dfw0, dfw1, None, None, None
 
 
 def spectral_conv(x, wl, bl, fw0, fw1, *, modes, act, two_d, x_transform=None):
     """x_transform: the (dropped-out) tensor fed to the transform when it differs from x."""
     xf = None if x_transform is None else x_transform.contiguous()
+    _note_use(wl, bl, fw0, fw1)
     return _SpectralConvFn.apply(x.contiguous(), xf, wl, bl, fw0, fw1, int(modes), ACT[act], bool(two_d))
