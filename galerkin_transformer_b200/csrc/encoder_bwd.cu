@@ -82,41 +82,6 @@ __device__ __forceinline__ void split_tile_affine(uint8_t* tile, int r, int kc, 
         *reinterpret_cast<uint4*>(bb + unit_off(r, u)) = l;
     }
 }
-// attention-matrix-shaped reduction shared with the forward: out[e] = mask * scale * sum_k part[k][e], e < 4 d d
-__device__ __forceinline__ void reduce_attn_partials(const float* __restrict__ pb, int tiles, int ne, int wt, float scale,
-                                                     const unsigned char* keep_mask, float mask_p, unsigned long long mseed,
-                                                     long long e_base, float* As) {
-    constexpr int EPT = (NH * 34 * 34 + NWORK * 32 - 1) / (NWORK * 32);
-    float acc[EPT];
-#pragma unroll
-    for (int i = 0; i < EPT; ++i) acc[i] = 0.f;
-    // four tiles' loads in flight per round (76 independent loads per thread); tile order of the sum is fixed
-    for (int k = 0; k < tiles; k += 4) {
-        const float* p0 = pb + (long long)k * ne;
-        float t[4][EPT];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int i = 0; i < EPT; ++i) {
-                const int e = wt + i * NWORK * 32;
-                t[j][i] = (k + j < tiles && e < ne) ? __ldg(p0 + (long long)j * ne + e) : 0.f;
-            }
-#pragma unroll
-        for (int i = 0; i < EPT; ++i) acc[i] = (((acc[i] + t[0][i]) + t[1][i]) + t[2][i]) + t[3][i];
-    }
-#pragma unroll
-    for (int i = 0; i < EPT; ++i) {
-        const int e = wt + i * NWORK * 32;
-        if (e < ne) {
-            float s = acc[i] * scale;
-            const long long E = e_base + e;
-            if (keep_mask) s *= 2.f * (float)keep_mask[E];
-            else if (mask_p > 0.f) s *= dropout_scale(mask_p, mseed, (unsigned long long)E);
-            As[e] = s;
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // kernel B1: feed-forward backward
 // ---------------------------------------------------------------------------------------------------------------
@@ -585,6 +550,7 @@ __global__ void __launch_bounds__(THREADS, 1) enc_kv_bwd_kernel(const __grid_con
         mbar_init(&bar->xfull, 1);
         mbar_init(&bar->done, 1);
         for (int i = 0; i < 4; ++i) { mbar_init(&bar->dfull[i], 1); mbar_init(&bar->hand[i], NWORK); }
+        partials_init(bar);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapQKV) : "memory");
     }
@@ -597,6 +563,8 @@ __global__ void __launch_bounds__(THREADS, 1) enc_kv_bwd_kernel(const __grid_con
         if (lane == 0) {
             mbar_expect_tx(&bar->xfull, 4 * TILE_BYTES);
             for (int j = 0; j < 4; ++j) tma_load_3d(RK + j * TILE_BYTES, &mapQKV, &bar->xfull, 128 + 32 * j, t0, b);
+            // tile partials of G stream through the V tile's (not yet needed) shared memory, then V lands there
+            partials_produce(bar, RV, a.gpart + (long long)b * a.tiles * NH * dd, a.tiles, NH * dd);
             mbar_expect_tx(&bar->done, 4 * TILE_BYTES);
             for (int j = 0; j < 4; ++j) tma_load_3d(RV + j * TILE_BYTES, &mapQKV, &bar->done, 256 + 32 * j, t0, b);
         }
@@ -638,8 +606,21 @@ __global__ void __launch_bounds__(THREADS, 1) enc_kv_bwd_kernel(const __grid_con
         {
             unsigned long long mseed = a.mask_seed;
             if (a.mask_p > 0.f && a.seed_off) mseed += *a.seed_off;
-            reduce_attn_partials(a.gpart + (long long)b * a.tiles * NH * dd, a.tiles, NH * dd, wt, a.scale, a.keep_mask,
-                                 a.mask_p, mseed, (long long)b * NH * dd, dAs);
+            constexpr int EPT = (NH * 34 * 34 + NWORK * 32 - 1) / (NWORK * 32);
+            float acc[EPT];
+            const int ne = NH * dd;
+            partials_consume<EPT>(bar, RV, a.tiles, ne, wt, lane, acc);
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) {
+                const int e = wt + i * NWORK * 32;
+                if (e < ne) {
+                    float sv = acc[i] * a.scale;
+                    const long long E = (long long)b * ne + e;
+                    if (a.keep_mask) sv *= 2.f * (float)a.keep_mask[E];
+                    else if (a.mask_p > 0.f) sv *= dropout_scale(a.mask_p, mseed, (unsigned long long)E);
+                    dAs[e] = sv;
+                }
+            }
         }
         worker_bar();
         if (wt == 0) trace(10);

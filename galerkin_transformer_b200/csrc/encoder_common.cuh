@@ -331,6 +331,53 @@ struct Bars {
     uint32_t tmem_slot;
 };
 
+// ---- tile-partial reduction through shared memory -------------------------------------------------------------------
+// The per-sample attention-shaped matrices (4 x d x d) are summed over the sample's tiles in TILE ORDER (deterministic).
+// One producer lane streams the 15 x 18.5 KB of partials through a 3-slot ring with 1-D bulk copies
+// (Bars::full/empty[3..5]) and the workers add slot after slot from shared memory -- no registers tied up in flight.
+// The step is L2-bandwidth bound: all 120 CTAs pull their sample's partials at once (33 MB per kernel, ~9 us either way).
+// Summing once per sample instead (the tile CTA that finishes last, ticket counter) was built and measured: its serial
+// tail on the previous kernel costs more than the 15-fold traffic it saves (3.89 vs 3.82 ms per C3 step); so was a
+// cluster-of-15 DSMEM reduction (only 7 such clusters fit the GPU at one CTA per SM, tools/probes/cluster_probe.cu).
+constexpr int PART_SLOTS = 3;
+constexpr int PART_SLOT_BYTES = 18560;                       // >= 4 * 34 * 34 * 4, multiple of 128
+
+__device__ __forceinline__ void partials_init(Bars* bar) {   // by the thread that initialises the other barriers
+    for (int s = 0; s < PART_SLOTS; ++s) { mbar_init(&bar->full[3 + s], 1); mbar_init(&bar->empty[3 + s], NWORK); }
+}
+__device__ __forceinline__ void partials_produce(Bars* bar, uint8_t* pbuf, const float* pb, int tiles, int ne) {
+    const uint32_t bytes = (uint32_t)ne * 4u;
+    for (int k = 0; k < tiles; ++k) {
+        const int s = k % PART_SLOTS;
+        mbar_wait(&bar->empty[3 + s], ((k / PART_SLOTS) & 1) ^ 1);
+        mbar_expect_tx(&bar->full[3 + s], bytes);
+        bulk_load(pbuf + s * PART_SLOT_BYTES, pb + (long long)k * ne, bytes, &bar->full[3 + s]);
+    }
+    // the ring memory is reused afterwards: wait until the workers have read the last fill of every slot
+    for (int s = 0; s < PART_SLOTS && s < tiles; ++s) {
+        const int uses = (tiles - s + PART_SLOTS - 1) / PART_SLOTS;
+        mbar_wait(&bar->empty[3 + s], (uses - 1) & 1);
+    }
+}
+template <int EPT>
+__device__ __forceinline__ void partials_consume(Bars* bar, const uint8_t* pbuf, int tiles, int ne, int wt, int lane,
+                                                 float (&acc)[EPT]) {
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) acc[i] = 0.f;
+    for (int k = 0; k < tiles; ++k) {
+        const int s = k % PART_SLOTS;
+        mbar_wait(&bar->full[3 + s], (k / PART_SLOTS) & 1);
+        const float* pslot = reinterpret_cast<const float*>(pbuf + s * PART_SLOT_BYTES);
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            const int e = wt + i * NWORK * 32;
+            if (e < ne) acc[i] += pslot[e];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar->empty[3 + s]);
+    }
+}
+
 static inline bool make_tile_map(CUtensorMap* m, const float* base, int ld, int n, int B) {
     cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)n, (cuuint64_t)B};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)ld * 4 * (cuuint64_t)n};

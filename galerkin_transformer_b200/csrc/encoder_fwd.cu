@@ -315,6 +315,7 @@ __global__ void __launch_bounds__(THREADS, 1) enc_attn_kernel(const __grid_const
         mbar_init(&bar->xconv, NWORK);
         for (int s = 0; s < ATT_RING; ++s) { mbar_init(&bar->full[s], 1); mbar_init(&bar->empty[s], 1); }
         for (int i = 0; i < 4; ++i) { mbar_init(&bar->dfull[i], 1); mbar_init(&bar->hand[i], NWORK); }
+        partials_init(bar);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapQ) : "memory");
     }
@@ -329,6 +330,8 @@ __global__ void __launch_bounds__(THREADS, 1) enc_attn_kernel(const __grid_const
         if (lane == 0) {
             mbar_expect_tx(&bar->xfull, 4 * TILE_BYTES);
             for (int j = 0; j < 4; ++j) tma_load_3d(R + j * TILE_BYTES, &mapQ, &bar->xfull, 32 * j, t0, b);
+            // tile partials of the attention matrix through the (still idle) weight ring + staging area
+            partials_produce(bar, ring, a.part + (long long)b * a.tiles * NH * dd, a.tiles, NH * dd);
             for (int i = 0; i < 6; ++i) {
                 const int s = i % ATT_RING;
                 mbar_wait(&bar->empty[s], ((i / ATT_RING) & 1) ^ 1);
@@ -385,27 +388,11 @@ __global__ void __launch_bounds__(THREADS, 1) enc_attn_kernel(const __grid_const
         {
             unsigned long long mseed = a.mask_seed;
             if (a.mask_p > 0.f && a.seed_off) mseed += *a.seed_off;
-            const float* pb = a.part + (long long)b * a.tiles * NH * dd;
-            // every thread owns <= 19 elements; the tile partials are summed in tile order (deterministic) with all of a
-            // tile's loads in flight at once
+            // every thread owns <= 19 elements; the tile partials arrive slot by slot in tile order (deterministic sum)
             constexpr int EPT = (NH * 34 * 34 + NWORK * 32 - 1) / (NWORK * 32);
             float acc[EPT];
-#pragma unroll
-            for (int i = 0; i < EPT; ++i) acc[i] = 0.f;
             const int ne = NH * dd;
-            for (int k = 0; k < a.tiles; k += 4) {
-                const float* p0 = pb + (long long)k * ne;
-                float t[4][EPT];
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int i = 0; i < EPT; ++i) {
-                        const int e = wt + i * NWORK * 32;
-                        t[j][i] = (k + j < a.tiles && e < ne) ? __ldg(p0 + (long long)j * ne + e) : 0.f;
-                    }
-#pragma unroll
-                for (int i = 0; i < EPT; ++i) acc[i] = (((acc[i] + t[0][i]) + t[1][i]) + t[2][i]) + t[3][i];
-            }
+            partials_consume<EPT>(bar, ring, a.tiles, ne, wt, lane, acc);
 #pragma unroll
             for (int i = 0; i < EPT; ++i) {
                 const int e = wt + i * NWORK * 32;
