@@ -478,6 +478,25 @@ __global__ void tc_splitk_reduce_group_kernel(const __grid_constant__ TcGroup G)
     const TcArgs& g = G.g[blockIdx.y];
     if (g.ksplit <= 1) return;          // that problem's CTAs wrote the final values themselves
     const long long total = (long long)g.M * g.N;
+    if (g.vec4) {       // float4 columns, eight split partials in flight per thread; the sum stays in split order (deterministic)
+        const float4* w4 = reinterpret_cast<const float4*>(g.ws);
+        const long long total4 = total / 4;
+        const int n4 = g.N / 4;
+        for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total4; e += (long long)gridDim.x * blockDim.x) {
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k0 = 0; k0 < g.ksplit; k0 += 8) {
+                float4 v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    v[j] = k0 + j < g.ksplit ? w4[(long long)(k0 + j) * total4 + e] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { s.x += v[j].x; s.y += v[j].y; s.z += v[j].z; s.w += v[j].w; }
+            }
+            const int m = (int)(e / n4), n = (int)(e % n4) * 4;
+            *reinterpret_cast<float4*>(g.ep.C + (long long)m * g.ep.ldc + n) = s;
+        }
+        return;
+    }
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const int n = (int)(e % g.N);
         const int m = (int)(e / g.N);
