@@ -587,7 +587,7 @@ extern "C" int gb200_conv1_fwd(int device, const float* x, const float* w, float
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     static const int rows_on = [] { const char* v = getenv("GB200_CONV1_ROWS"); return v ? atoi(v) : 1; }();
-    if (rows_on && C <= 128 && W <= 4096) {
+    if (rows_on && C <= 128 && W <= 2048) {
         int rb = B * H;
         if (rb > 148 * 16) rb = 148 * 16;
         conv1_fwd_row_kernel<<<rb, 256, 3 * (W + 2) * sizeof(float), as_stream(stream)>>>(a);

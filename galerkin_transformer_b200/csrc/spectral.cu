@@ -853,7 +853,7 @@ extern "C" int gb200_spectral_xdft(int device, const float* T1, int B, int n, in
     if (spectral_rows_enabled() && B <= 65535 && m <= 65535) {
         if (!inverse) {
             const size_t smem = (size_t)XD_RG * n * sizeof(float2);
-            if (smem <= 40 * 1024) {
+            if (smem <= 36 * 1024) {          // + 10.5 KB of static reduction buffer: stays under the 48 KB default limit
                 launch_pdl(xdft_rows_kernel, dim3(cdiv(2 * m, XD_RG), m, B), 32 * XD_XQ, smem, st,
                            reinterpret_cast<const float2*>(T1), n, m, C, reinterpret_cast<const float2*>(twX), scale,
                            reinterpret_cast<float2*>(out));

@@ -186,9 +186,7 @@ class FusedAdam:
         self.max_grad_norm = float(max_grad_norm)
         self.one_cycle = dict(one_cycle) if one_cycle else None
         self.step_count = 0
-        self._beta1_pow = 1.0                      # running product is wrong under a cycling beta1: recomputed per step
         self.hyper = torch.zeros(4, dtype=torch.float32, device=dev)
-        self._hyper_host = torch.zeros(4, dtype=torch.float32).pin_memory()
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
         self._ws_bytes = _lib.load().gb200_adam_clip_step_workspace_bytes(self.n)
         self._ws = torch.empty(max(1, (self._ws_bytes + 3) // 4), dtype=torch.float32, device=dev)
@@ -204,12 +202,10 @@ class FusedAdam:
         return lr, beta1, 1.0 - beta1 ** t, 1.0 - self.betas[1] ** t
 
     def set_hyper(self, k=None):
-        """Stage step k's hyper-parameters in the device array (async copy on the current stream)."""
+        """Stage step k's hyper-parameters in the device array (stream-ordered copy on the current stream)."""
         k = self.step_count if k is None else k
-        h = self.hyper_for_step(k)
-        for i in range(4):
-            self._hyper_host[i] = h[i]
-        self.hyper.copy_(self._hyper_host, non_blocking=True)
+        # a fresh pageable source: the runtime stages it at call time, so the host may run steps ahead of the device
+        self.hyper.copy_(torch.tensor(self.hyper_for_step(k), dtype=torch.float32))
 
     def launch(self, grads_packed=False):
         """clip + Adam on the flat buffers (graph-capturable: reads `self.hyper` from the device)."""
