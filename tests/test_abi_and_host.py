@@ -205,3 +205,33 @@ def test_resize_algorithm_restated_on_cpu(Hin, Win, Hout, Wout):
     gr = _resize_restated(cot.numpy(), Hout, Wout, backward_of=(2, Hin, Win, 3))
     assert np.abs(yr - y.detach().permute(0, 2, 3, 1).numpy()).max() < 1e-5
     assert np.abs(gr - gx.numpy()).max() < 1e-5
+
+
+def test_single_use_tracking_decides_when_side_stream_joins_may_be_deferred():
+    """functional._note_use / _single_use: a parameter-gradient side stream may stay unjoined until the end of backward only
+    if autograd will ADOPT the gradient tensor -- leaf parameter, used by exactly one node of the graph, no existing .grad."""
+    import torch
+    from galerkin_transformer_b200 import functional as GF
+    w, b = torch.nn.Parameter(torch.zeros(3)), torch.nn.Parameter(torch.zeros(3))
+    GF._note_use(w, b, None)
+    assert GF._single_use((w, b, None))                       # one forward use each, grads empty
+    assert GF._single_use((w,)) and w._gb200_total == 0       # counters are back to rest (a stray second call stays safe)
+    # a rollout: the same weight feeds three nodes; none of the three backward nodes may defer
+    for _ in range(3):
+        GF._note_use(w)
+    assert [GF._single_use((w,)) for _ in range(3)] == [False, False, False]
+    GF._note_use(w)
+    assert GF._single_use((w,))                               # next step: single use again
+    # an existing gradient means accumulation on the launching stream
+    w.grad = torch.ones(3)
+    GF._note_use(w)
+    assert not GF._single_use((w,))
+    w.grad = None
+    # non-leaf "parameters" (packed weights) are consumed by the next backward node right away
+    packed = torch.cat([w, b]) * 1.0
+    GF._note_use(packed)
+    assert not GF._single_use((packed,))
+    # no bookkeeping without grad mode (inference must not poison the counters)
+    with torch.no_grad():
+        GF._note_use(b)
+    assert getattr(b, "_gb200_pending", 0) == 0
