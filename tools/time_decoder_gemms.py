@@ -1,5 +1,6 @@
 """Stand-alone timings of the tall-skinny decoder GEMMs of C3 (M = 8*141*141 tokens) in the active precision mode:
-CUDA events around each launch, L2 flushed between launches.  Diagnostics only.
+CUDA events around each launch, L2 flushed between launches.  Diagnostics only (the event pair includes the host-side launch
+gap of the Python wrapper; these GEMMs are long enough, 35-60 us, for that not to matter much).
 
     python tools/time_decoder_gemms.py [--precision x3]"""
 import argparse

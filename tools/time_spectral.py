@@ -1,5 +1,7 @@
 """Stand-alone timings of the SpectralConv2d stages at the C3 decoder shape (B=8, n=141, C=32, 12 modes): CUDA events around each
-launch, L2 flushed between launches.  Diagnostics only.
+launch, L2 flushed between launches.  Diagnostics only -- and coarse: the event pair also brackets the host-side launch gap
+of the Python wrapper (~15-30 us), which dominates for kernels shorter than that; use tools/prof_step.py (CUPTI kernel
+durations) or ncu for per-kernel times.
 
     python tools/time_spectral.py"""
 import math
