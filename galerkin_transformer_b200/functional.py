@@ -10,6 +10,7 @@ import ctypes
 import os
 import math
 import threading
+import weakref
 
 import torch
 
@@ -162,7 +163,6 @@ def set_backward_streams(on):
 
 def _weak(t):
     """weak reference to an optional parameter tensor (autograd contexts must not keep non-saved tensors alive)"""
-    import weakref
     return (lambda: None) if t is None else weakref.ref(t)
 
 

@@ -4,7 +4,6 @@ of the Python wrapper (~15-30 us), which dominates for kernels shorter than that
 durations) or ncu for per-kernel times.
 
     python tools/time_spectral.py"""
-import math
 import os
 import sys
 
